@@ -1,0 +1,130 @@
+/*
+ * mnk_b200.h -- C ABI of libmnk_b200.so: the B200 (sm_100a) implementation of the batched MNK
+ * environment step, the self-play opponent turn and the rollout store of
+ * michal-szadkowski/rl-selfplay-mnk.
+ *
+ * The reference has no FFI layer (it is pure Python/PyTorch); each entry point below names the
+ * reference function it replaces (paths relative to the reference repo).  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer into caller-owned memory unless its name starts with
+ *     `host_`.  The library allocates no persistent device memory and keeps no global state.
+ *   - Every call is an asynchronous launch on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream).  No call synchronises except the *_host entry points, which say so.
+ *     All calls are CUDA-graph capturable except the *_host ones.
+ *   - Return value: 0 = ok; > 0 = a cudaError_t from the launch; < 0 = MNK_ERR_* argument error.
+ *   - bool tensors travel as uint8_t (torch.bool storage), 0 or 1.
+ *   - There is no CPU fallback: without a CUDA device every compute call returns a cudaError_t.
+ *
+ * Board state in HBM (struct mnk_state)
+ *   Each player's stones are a bitboard with ROW STRIDE n+1: bit (r*(n+1) + c) <=> cell (r, c); the
+ *   extra column is a permanently-zero guard that stops horizontal / diagonal lines from wrapping
+ *   across a row end.  A plane is `words` = ceil(m*(n+1)/64) uint64 words.  Planes are stored
+ *   structure-of-arrays so that one warp reads 32 consecutive envs' word w in one 256-byte request:
+ *       bits[(player * words + w) * num_envs + env]           player 0 = black, 1 = white
+ *       meta[env] = (move_count << 1) | current_player
+ */
+#ifndef MNK_B200_H
+#define MNK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNK_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#define MNK_OK 0
+#define MNK_ERR_NULL (-1)     /* a required pointer is NULL */
+#define MNK_ERR_GEOM (-2)     /* m, n, k unsupported: need 1 <= k <= min(m, n), n <= 32, m*(n+1) <= 512 */
+#define MNK_ERR_ALIGN (-3)    /* a buffer is not aligned as documented */
+#define MNK_ERR_ARG (-4)      /* other invalid argument (negative count, words mismatch, ...) */
+
+#define MNK_MAX_WORDS 8
+
+/* flags of mnk_step / mnk_step_host */
+#define MNK_STEP_ACTIONS_I32 1u /* `actions` is int32_t[] instead of int64_t[]                      */
+#define MNK_STEP_AUTORESET 2u   /* envs that finish are reset after their outputs are written:       */
+                                /* equals env.step(a) followed by env.reset(dones.nonzero())        */
+
+typedef struct mnk_state {
+    int32_t m, n, k;
+    int32_t words;     /* must equal mnk_state_words(m, n) */
+    int64_t num_envs;  /* envs held by THIS process (the local shard) */
+    uint64_t* bits;    /* u64[2][words][num_envs] */
+    uint32_t* meta;    /* u32[num_envs]           */
+} mnk_state_t;
+
+/* ---- introspection ------------------------------------------------------------------------ */
+int mnk_version(void);
+const char* mnk_error_string(int code);
+/* words per plane for an m x n board, or MNK_ERR_GEOM */
+int mnk_state_words(int m, int n);
+
+/* ---- environment: src/env/torch_vector_mnk_env.py ------------------------------------------ */
+
+/* TorchVectorMnkEnv.reset (torch_vector_mnk_env.py:34-42).  idx == NULL resets every env,
+ * otherwise the n_idx listed envs (player := black, move_count := 0).  The observe() the
+ * reference ends reset with is a separate mnk_observe call. */
+int mnk_reset(const mnk_state_t* st, const int64_t* idx, int64_t n_idx, void* stream);
+
+/* TorchVectorMnkEnv.observe (:46-53) fused with TorchSelfPlayWrapper._get_canonical_obs
+ * (src/selfplay/torch_self_play_wrapper.py:99-112).
+ *   obs   f32[num_envs][2][m][n] or NULL     mask  u8[num_envs][m*n] or NULL
+ *   swap  u8[num_envs] or NULL: envs with swap[e] != 0 get their two planes exchanged (the
+ *         "me first" canonical view of a white agent, :104-106)
+ *   fix_all_masked != 0: rows with no legal cell get mask[e][0] = 1 (:108-110) */
+int mnk_observe(const mnk_state_t* st, float* obs, uint8_t* mask, const uint8_t* swap,
+                int fix_all_masked, void* stream);
+
+/* TorchVectorMnkEnv.step / step_subset (:55-84) with _check_wins (:106-119) as shift-and-AND
+ * line tests.  For each listed env, in the reference's order: place the mover's stone
+ * unconditionally, ++move_count, win = mover has >= k in a row anywhere, draw = board full and
+ * no win, reward = 1.0 on a win, done = win | draw, toggle the player (also when done).
+ *   actions  i64[n_active] (i32 with MNK_STEP_ACTIONS_I32); values outside [0, m*n) place no stone
+ *   idx      NULL => dense step of envs 0..num_envs-1 (n_active must equal num_envs);
+ *            else i64[n_active] distinct env indices (step_subset)
+ *   rewards  f32[num_envs], dones u8[num_envs]: FULL SIZE, zero for unlisted envs
+ *   obs/mask as in mnk_observe (over ALL envs, after the step), either may be NULL
+ *   illegal  NULL, or int32[2] pre-zeroed: strict mode.  [0] counts moves onto an occupied or
+ *            out-of-range cell, [1] = 0x7fffffff - (the smallest offending env index), 0 = none.
+ *            The reference's validators (:86-104) are dead code, so the default (NULL) applies
+ *            such moves silently. */
+int mnk_step(const mnk_state_t* st, const void* actions, const int64_t* idx, int64_t n_active,
+             float* rewards, uint8_t* dones, float* obs, uint8_t* mask, int32_t* illegal,
+             uint32_t flags, void* stream);
+
+/* Same as the dense mnk_step but with HOST buffers (the end-to-end path a caller without device
+ * tensors uses): copies host_actions to dev_actions, steps, copies rewards / dones back and
+ * SYNCHRONISES the stream.  host_* should be pinned.  dev_* are caller-owned scratch:
+ * dev_actions i64|i32[num_envs], dev_rd = 5 * num_envs bytes (f32 rewards then u8 dones);
+ * host_rd receives the same 5 * num_envs bytes.  obs / mask stay on the device (may be NULL). */
+int mnk_step_host(const mnk_state_t* st, const void* host_actions, void* dev_actions, void* dev_rd,
+                  void* host_rd, float* obs, uint8_t* mask, uint32_t flags, void* stream);
+
+/* `env.boards` (torch_vector_mnk_env.py:17) as a writable f32[num_envs][2][m][n] mirror:
+ * unpack = bitboards -> f32 planes, pack = f32 planes (non-zero = stone) -> bitboards. */
+int mnk_unpack_boards(const mnk_state_t* st, float* boards, void* stream);
+int mnk_pack_boards(const mnk_state_t* st, const float* boards, void* stream);
+
+/* `env.current_player` / `env.move_counts` (:18-19) as i64[num_envs]; either pointer may be NULL. */
+int mnk_export_meta(const mnk_state_t* st, int64_t* current_player, int64_t* move_counts, void* stream);
+int mnk_import_meta(const mnk_state_t* st, const int64_t* current_player, const int64_t* move_counts,
+                    void* stream);
+
+/* ---- policies: src/selfplay/policy.py -------------------------------------------------------- */
+
+/* RandomPolicy.act (policy.py:13-29) straight from the bitboards: a uniformly random empty cell
+ * per env (all cells when the board is full), deterministic != 0 => the first empty cell (:26-27).
+ * Counter-based Philox4x32-10 keyed by `seed`, indexed by (env_offset + env, counter): results do
+ * not depend on how envs are sharded over GPUs.  actions i64[num_envs]. */
+int mnk_random_legal(const mnk_state_t* st, uint64_t seed, uint64_t counter, int64_t env_offset,
+                     int deterministic, int64_t* actions, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MNK_B200_H */

@@ -1,0 +1,62 @@
+// mnk_dispatch.cuh -- host-side helpers: argument validation, geometry dispatch, launch shapes.
+#pragma once
+#include "mnk_device.cuh"
+
+// Geometries compiled with every loop bound and shift distance constant.  Anything else runs the
+// same templates with a runtime geometry (DGeom<words>).
+#define MNK_STATIC_GEOMS(X) X(3, 3, 3) X(9, 9, 5) X(13, 13, 5) X(15, 15, 5) X(19, 19, 5)
+
+static inline int mnk_words_for(int m, int n) {
+    if (m < 1 || n < 1 || n > 32) return MNK_ERR_GEOM;
+    const long long bits = (long long)m * (n + 1);
+    if (bits > 64LL * MNK_MAX_WORDS) return MNK_ERR_GEOM;
+    return (int)((bits + 63) / 64);
+}
+
+static inline int mnk_check_state(const mnk_state_t* st) {
+    if (st == nullptr || st->bits == nullptr || st->meta == nullptr) return MNK_ERR_NULL;
+    const int words = mnk_words_for(st->m, st->n);
+    if (words < 0) return words;
+    if (st->k < 1 || st->k > st->m || st->k > st->n) return MNK_ERR_GEOM;
+    if (words != st->words || st->num_envs < 0) return MNK_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(st->bits) & 7u) || (reinterpret_cast<uintptr_t>(st->meta) & 3u))
+        return MNK_ERR_ALIGN;
+    return MNK_OK;
+}
+
+// calls f(geom) with the matching SGeom<> / DGeom<> value; f returns int
+template <class F>
+static inline int mnk_dispatch_geom(const mnk_state_t& st, F&& f) {
+#define MNK_TRY_STATIC(M, N, K) \
+    if (st.m == M && st.n == N && st.k == K) return f(SGeom<M, N, K>{});
+    MNK_STATIC_GEOMS(MNK_TRY_STATIC)
+#undef MNK_TRY_STATIC
+    switch (st.words) {
+        case 1: return f(DGeom<1>{st.m, st.n, st.k});
+        case 2: return f(DGeom<2>{st.m, st.n, st.k});
+        case 3: return f(DGeom<3>{st.m, st.n, st.k});
+        case 4: return f(DGeom<4>{st.m, st.n, st.k});
+        case 5: return f(DGeom<5>{st.m, st.n, st.k});
+        case 6: return f(DGeom<6>{st.m, st.n, st.k});
+        case 7: return f(DGeom<7>{st.m, st.n, st.k});
+        case 8: return f(DGeom<8>{st.m, st.n, st.k});
+        default: return MNK_ERR_GEOM;
+    }
+}
+
+static inline int mnk_launch_status() {
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MNK_OK : (int)e;
+}
+
+// warp-tile kernels: one warp per 32 consecutive envs, 4 warps per CTA
+constexpr int kTileEnvs = 32;
+constexpr int kTileWarps = 4;
+constexpr int kTileThreads = kTileWarps * 32;
+static inline unsigned mnk_tile_blocks(long long num_envs) {
+    const long long tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
+    return (unsigned)((tiles + kTileWarps - 1) / kTileWarps);
+}
+// thread-per-env kernels
+constexpr int kFlatThreads = 256;
+static inline unsigned mnk_flat_blocks(long long count) { return (unsigned)((count + kFlatThreads - 1) / kFlatThreads); }

@@ -1,0 +1,11 @@
+"""mnk_b200 -- B200 (sm_100a) implementation of the rl-selfplay-mnk hot path.
+
+Host side: PyTorch tensors for memory / streams / torch.distributed; compute: hand-written CUDA
+kernels in libmnk_b200.so behind the C ABI of include/mnk_b200.h.  The sibling packages ``env/``
+and ``selfplay/`` re-export these classes under the reference's module paths so that putting
+``rl-selfplay-mnk_b200/`` ahead of the reference's ``src/`` on sys.path swaps the path in.
+"""
+from ._lib import build, lib, LIB_PATH  # noqa: F401
+from .env import TorchVectorMnkEnv  # noqa: F401
+
+__all__ = ["build", "lib", "LIB_PATH", "TorchVectorMnkEnv"]

@@ -1,0 +1,116 @@
+"""ctypes binding of libmnk_b200.so (C ABI declared in include/mnk_b200.h).
+
+The library is built in-tree (``build()``: nvcc, sm_100a only) and loaded from
+``rl-selfplay-mnk_b200/libmnk_b200.so``.  There is NO fallback: if the shared object is
+missing or a call fails, a RuntimeError / ValueError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+from typing import Optional
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # rl-selfplay-mnk_b200/
+_CSRC = os.path.join(_PKG_ROOT, "csrc")
+_OBJ = os.path.join(_PKG_ROOT, "build")
+LIB_PATH = os.path.join(_PKG_ROOT, "libmnk_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--std=c++17",
+    "-Xcompiler", "-fPIC",
+]
+
+MNK_OK, MNK_ERR_NULL, MNK_ERR_GEOM, MNK_ERR_ALIGN, MNK_ERR_ARG = 0, -1, -2, -3, -4
+STEP_ACTIONS_I32, STEP_AUTORESET = 1, 2
+
+
+class MnkState(ctypes.Structure):
+    """struct mnk_state of include/mnk_b200.h."""
+    _fields_ = [("m", ctypes.c_int32), ("n", ctypes.c_int32), ("k", ctypes.c_int32), ("words", ctypes.c_int32),
+                ("num_envs", ctypes.c_int64), ("bits", ctypes.c_void_p), ("meta", ctypes.c_void_p)]
+
+
+def sources():
+    return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cu"))
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)]
+    deps.append(os.path.join(os.path.dirname(_PKG_ROOT), "include", "mnk_b200.h"))
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every csrc/*.cu for sm_100a and link libmnk_b200.so (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    os.makedirs(_OBJ, exist_ok=True)
+
+    def compile_one(src: str) -> str:
+        obj = os.path.join(_OBJ, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, sources()))
+    cmd = [nvcc, *NVCC_FLAGS, "-shared", "-o", LIB_PATH, *objs]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+_VP, _I32, _I64, _U32, _U64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64
+_ST = ctypes.POINTER(MnkState)
+
+# name -> (restype, argtypes); must list every symbol include/mnk_b200.h declares
+SIGNATURES = {
+    "mnk_version": (_I32, []),
+    "mnk_error_string": (ctypes.c_char_p, [_I32]),
+    "mnk_state_words": (_I32, [_I32, _I32]),
+    "mnk_reset": (_I32, [_ST, _VP, _I64, _VP]),
+    "mnk_observe": (_I32, [_ST, _VP, _VP, _VP, _I32, _VP]),
+    "mnk_step": (_I32, [_ST, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
+    "mnk_step_host": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
+    "mnk_unpack_boards": (_I32, [_ST, _VP, _VP]),
+    "mnk_pack_boards": (_I32, [_ST, _VP, _VP]),
+    "mnk_export_meta": (_I32, [_ST, _VP, _VP, _VP]),
+    "mnk_import_meta": (_I32, [_ST, _VP, _VP, _VP]),
+    "mnk_random_legal": (_I32, [_ST, _U64, _U64, _I64, _I32, _VP, _VP]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library.  Raises if it has not been built -- there is no CPU or eager fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  mnk_b200 has no CPU / eager fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)     # AttributeError => stale library
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(code: int, what: str = "mnk") -> None:
+    if code == MNK_OK:
+        return
+    msg = lib().mnk_error_string(code).decode()
+    if code in (MNK_ERR_GEOM, MNK_ERR_ARG, MNK_ERR_ALIGN, MNK_ERR_NULL):
+        raise ValueError(f"{what}: {msg} (code {code})")
+    raise RuntimeError(f"{what}: CUDA error {code}: {msg}")

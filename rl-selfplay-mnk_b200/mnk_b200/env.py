@@ -1,0 +1,250 @@
+"""TorchVectorMnkEnv on packed bitboards and sm_100a kernels.
+
+Drop-in for the reference's ``src/env/torch_vector_mnk_env.py:7-119``: same constructor,
+attributes (``m n k num_envs device max_moves env_indices boards current_player
+move_counts``), methods and return tensors (``observation`` f32[N,2,m,n], ``action_mask``
+bool[N,m*n], ``rewards`` f32[N], ``dones`` bool[N]).  The state itself lives in HBM as two
+guard-strided bitboards per env plus one u32 of (move_count, player) -- see
+include/mnk_b200.h -- and every operation is one launch of libmnk_b200.so on the current
+torch CUDA stream with no host synchronisation.
+
+``boards``, ``current_player`` and ``move_counts`` are materialised lazily as *live mirrors*
+the first time they are read: from then on every operation first folds the mirror back
+into the bitboards (so writes such as ``env.boards[0, 0, 0, 0] = 1`` in the reference's
+tests take effect) and refreshes it afterwards (so a held reference stays current).  The
+training hot path never touches them and pays nothing.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import MnkState, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class TorchVectorMnkEnv:
+    def __init__(self, m: int, n: int, k: int, num_envs: int, device: str = "cuda", strict: bool = False,
+                 env_offset: int = 0):
+        assert m >= k and n >= k, f"Board ({m}x{n}) is too small for k={k}"   # reference :9
+        self.m, self.n, self.k = int(m), int(n), int(k)
+        self.num_envs = int(num_envs)
+        self.device = device
+        self._dev = torch.device(device)
+        if self._dev.type != "cuda":
+            raise RuntimeError("mnk_b200 runs on sm_100a CUDA devices only (no CPU fallback); "
+                               f"got device={device!r}")
+        if self._dev.index is None:
+            self._dev = torch.device("cuda", torch.cuda.current_device())
+        self._L = _lib.lib()
+        words = self._L.mnk_state_words(self.m, self.n)
+        check(words if words < 0 else 0, "TorchVectorMnkEnv")
+        self.strict = bool(strict)
+        self.env_offset = int(env_offset)     # global id of local env 0 (sharded runs)
+        self.max_moves = self.m * self.n
+        self.env_indices = torch.arange(self.num_envs, device=self._dev)
+        # packed state: bits i64[2, words, N] (bit patterns of u64), meta i32[N]
+        self._bits = torch.zeros((2, words, self.num_envs), dtype=torch.int64, device=self._dev)
+        self._meta = torch.zeros(self.num_envs, dtype=torch.int32, device=self._dev)
+        self._st = MnkState(self.m, self.n, self.k, words, self.num_envs, self._bits.data_ptr(), self._meta.data_ptr())
+        self._stp = ctypes.byref(self._st)
+        self._boards_mirror: Optional[torch.Tensor] = None
+        self._player_mirror: Optional[torch.Tensor] = None
+        self._count_mirror: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return torch.cuda.current_stream(self._dev).cuda_stream
+
+    def _call(self, fn, *args):
+        if torch.cuda.current_device() != self._dev.index:
+            with torch.cuda.device(self._dev):
+                check(fn(self._stp, *args, self._stream()), fn.__name__)
+        else:
+            check(fn(self._stp, *args, self._stream()), fn.__name__)
+
+    def _fold_mirrors(self):
+        """Mirror tensors the caller may have written -> packed state."""
+        if self._boards_mirror is not None:
+            self._call(self._L.mnk_pack_boards, _ptr(self._boards_mirror))
+        if self._player_mirror is not None or self._count_mirror is not None:
+            self._call(self._L.mnk_import_meta, _ptr(self._player_mirror), _ptr(self._count_mirror))
+
+    def _refresh_mirrors(self):
+        if self._boards_mirror is not None:
+            self._call(self._L.mnk_unpack_boards, _ptr(self._boards_mirror))
+        if self._player_mirror is not None or self._count_mirror is not None:
+            self._call(self._L.mnk_export_meta, _ptr(self._player_mirror), _ptr(self._count_mirror))
+
+    # ------------------------------------------------------------------ reference attributes
+    @property
+    def boards(self) -> torch.Tensor:
+        """f32[N,2,m,n] one-hot planes (reference :17); a live, writable mirror."""
+        if self._boards_mirror is None:
+            self._boards_mirror = torch.empty((self.num_envs, 2, self.m, self.n), dtype=torch.float32, device=self._dev)
+            self._call(self._L.mnk_unpack_boards, _ptr(self._boards_mirror))
+        return self._boards_mirror
+
+    @boards.setter
+    def boards(self, value: torch.Tensor):
+        self.boards.copy_(value)
+
+    @property
+    def current_player(self) -> torch.Tensor:
+        """i64[N] side to move (reference :18); a live, writable mirror."""
+        if self._player_mirror is None:
+            self._player_mirror = torch.empty(self.num_envs, dtype=torch.long, device=self._dev)
+            self._call(self._L.mnk_export_meta, _ptr(self._player_mirror), None)
+        return self._player_mirror
+
+    @current_player.setter
+    def current_player(self, value: torch.Tensor):
+        self.current_player.copy_(value)
+
+    @property
+    def move_counts(self) -> torch.Tensor:
+        """i64[N] plies played (reference :19); a live, writable mirror."""
+        if self._count_mirror is None:
+            self._count_mirror = torch.empty(self.num_envs, dtype=torch.long, device=self._dev)
+            self._call(self._L.mnk_export_meta, None, _ptr(self._count_mirror))
+        return self._count_mirror
+
+    @move_counts.setter
+    def move_counts(self, value: torch.Tensor):
+        self.move_counts.copy_(value)
+
+    def release_mirrors(self):
+        """Drop the lazily created boards / current_player / move_counts mirrors (after folding any
+        writes back), returning the env to the zero-overhead packed mode."""
+        self._fold_mirrors()
+        self._boards_mirror = self._player_mirror = self._count_mirror = None
+
+    # ------------------------------------------------------------------ reference methods
+    def _new_obs(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        obs = torch.empty((self.num_envs, 2, self.m, self.n), dtype=torch.float32, device=self._dev)
+        mask = torch.empty((self.num_envs, self.m * self.n), dtype=torch.bool, device=self._dev)
+        return obs, mask
+
+    def reset(self, env_indices: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """reference :34-44"""
+        self._fold_mirrors()
+        if env_indices is None:
+            self._call(self._L.mnk_reset, None, 0)
+        else:
+            idx = torch.as_tensor(env_indices, device=self._dev).to(torch.long).contiguous()
+            self._call(self._L.mnk_reset, _ptr(idx), idx.numel())
+        self._refresh_mirrors()
+        return self._observe_packed()
+
+    def _observe_packed(self, swap: Optional[torch.Tensor] = None, fix_all_masked: bool = False):
+        obs, mask = self._new_obs()
+        self._call(self._L.mnk_observe, _ptr(obs), _ptr(mask), _ptr(swap), int(fix_all_masked))
+        return {"observation": obs, "action_mask": mask}
+
+    def observe(self) -> Dict[str, torch.Tensor]:
+        """reference :46-53 -- fresh tensors every call (callers mutate them)."""
+        self._fold_mirrors()
+        return self._observe_packed()
+
+    def step(self, actions: torch.Tensor):
+        """reference :55-58"""
+        return self._step(actions, None)
+
+    def step_subset(self, actions: torch.Tensor, active_indices: torch.Tensor):
+        """reference :60-84 -- rewards / dones are full-size [N], zero for unlisted envs."""
+        return self._step(actions, active_indices)
+
+    def _prep_actions(self, actions: torch.Tensor) -> Tuple[torch.Tensor, int]:
+        a = torch.as_tensor(actions, device=self._dev)
+        if a.dtype == torch.int32:
+            return a.contiguous(), _lib.STEP_ACTIONS_I32
+        return a.to(torch.long).contiguous(), 0
+
+    def _step(self, actions, active_indices, autoreset: bool = False, materialise: bool = True,
+              out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        self._fold_mirrors()
+        a, flags = self._prep_actions(actions)
+        idx = None
+        if active_indices is not None:
+            idx = torch.as_tensor(active_indices, device=self._dev).to(torch.long).contiguous()
+            if a.numel() != idx.numel():
+                raise ValueError(f"step_subset: {a.numel()} actions for {idx.numel()} indices")
+        elif a.numel() != self.num_envs:
+            raise ValueError(f"step: expected {self.num_envs} actions, got {a.numel()}")
+        if self.strict:
+            self._validate(a, idx)
+        if autoreset:
+            flags |= _lib.STEP_AUTORESET
+        rewards = torch.empty(self.num_envs, dtype=torch.float32, device=self._dev)
+        dones = torch.empty(self.num_envs, dtype=torch.bool, device=self._dev)
+        obs = mask = None
+        if out is not None:
+            obs, mask = out
+        elif materialise:
+            obs, mask = self._new_obs()
+        self._call(self._L.mnk_step, _ptr(a), _ptr(idx), a.numel(), _ptr(rewards), _ptr(dones), _ptr(obs), _ptr(mask),
+                   None, flags)
+        self._refresh_mirrors()
+        return {"observation": obs, "action_mask": mask}, rewards, dones
+
+    def _validate(self, a: torch.Tensor, idx: Optional[torch.Tensor]):
+        """Opt-in legality check with the reference's (dead-code) messages, :86-104."""
+        cells = self.m * self.n
+        bad = (a < 0) | (a >= cells)
+        if bad.any():
+            val = a[torch.nonzero(bad)[0]].item()
+            raise ValueError(f"Action out of bounds! Env received {val}, expected [0, {cells - 1}]")
+        mask = self._observe_packed()["action_mask"]
+        rows = self.env_indices if idx is None else idx
+        occupied = ~mask[rows, a.long()]
+        if occupied.any():
+            env_id = rows[torch.nonzero(occupied)[0]].item()
+            raise ValueError(f"Illegal Move: Env {env_id} tried to play in occupied cell.")
+
+    # ------------------------------------------------------------------ extensions (not in the reference)
+    def step_autoreset(self, actions: torch.Tensor, materialise: bool = True, out=None):
+        """env.step(actions) followed by env.reset(dones.nonzero()) as ONE launch: the returned
+        observation is the reference's step() observation (terminal boards included); finished envs
+        are empty boards from the next call on."""
+        return self._step(actions, None, autoreset=True, materialise=materialise, out=out)
+
+    def random_legal_actions(self, seed: int, counter: int, deterministic: bool = False,
+                             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """RandomPolicy.act (src/selfplay/policy.py:13-29) straight from the bitboards."""
+        self._fold_mirrors()
+        if out is None:
+            out = torch.empty(self.num_envs, dtype=torch.long, device=self._dev)
+        self._call(self._L.mnk_random_legal, seed & (2**64 - 1), counter, self.env_offset, int(deterministic), _ptr(out))
+        return out
+
+    def step_host(self, host_actions: torch.Tensor, host_out: torch.Tensor, autoreset: bool = False,
+                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        """End-to-end step for callers holding HOST buffers: pinned int64 actions in, pinned
+        rewards/dones bytes out (5*N bytes: f32 rewards then u8 dones), one H2D + launch + D2H +
+        stream sync inside libmnk_b200 (mnk_step_host).  Observation / mask stay on the device."""
+        self._fold_mirrors()
+        if not hasattr(self, "_dev_actions"):
+            self._dev_actions = torch.empty(self.num_envs, dtype=torch.long, device=self._dev)
+            self._dev_rd = torch.empty(5 * self.num_envs, dtype=torch.uint8, device=self._dev)
+        flags = _lib.STEP_AUTORESET if autoreset else 0
+        if host_actions.dtype == torch.int32:
+            flags |= _lib.STEP_ACTIONS_I32
+        obs, mask = out if out is not None else self._new_obs()
+        self._call(self._L.mnk_step_host, _ptr(host_actions), _ptr(self._dev_actions), _ptr(self._dev_rd),
+                   _ptr(host_out), _ptr(obs), _ptr(mask), flags)
+        self._refresh_mirrors()
+        n = self.num_envs
+        return {"observation": obs, "action_mask": mask}, host_out[:4 * n].view(torch.float32), host_out[4 * n:].view(torch.bool)
+
+    def state_checksum(self) -> int:
+        """Order-sensitive 64-bit digest of the packed state (used by bench.py / tests)."""
+        self._fold_mirrors()
+        w = torch.arange(1, self._bits.numel() + 1, device=self._dev, dtype=torch.long)
+        h = (self._bits.reshape(-1) * w).sum() + (self._meta.long() * (w[: self.num_envs] * 31 + 7)).sum()
+        return int(h.item()) & (2**64 - 1)

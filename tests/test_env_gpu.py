@@ -1,0 +1,225 @@
+"""GPU parity tests of the env kernels: golden traces recorded from the reference, the CPU
+oracle on larger seeded batches, and size-independent properties at BASELINE sizes.
+All comparisons are bit-exact (torch.equal / np.array_equal)."""
+import numpy as np
+import pytest
+import torch
+
+import golden_io as gio
+from oracle import mnk_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def make_env(*a, **kw):
+    from env.torch_vector_mnk_env import TorchVectorMnkEnv
+    return TorchVectorMnkEnv(*a, device=DEV, **kw)
+
+
+def t(x, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(x), device=DEV) if dtype is None else torch.as_tensor(np.ascontiguousarray(x), device=DEV, dtype=dtype)
+
+
+@pytest.mark.parametrize("mirrors", [False, True], ids=["packed", "mirrors"])
+@pytest.mark.parametrize("path", gio.files("env_trace_"), ids=gio.name)
+def test_golden_env_trace(path, mirrors):
+    g = gio.load(path)
+    m, n, k, ne = (int(x) for x in g["geom"])
+    env = make_env(m, n, k, ne)
+    env.reset()
+    if mirrors:
+        held = (env.boards, env.current_player, env.move_counts)     # live mirrors stay current
+    for step in range(len(g["op"])):
+        op, active, actions = int(g["op"][step]), g["active"][step], g["actions"][step]
+        idx = np.nonzero(active)[0]
+        rewards = torch.zeros(ne, device=DEV)
+        dones = torch.zeros(ne, dtype=torch.bool, device=DEV)
+        if op == gio.OP_RESET_ALL:
+            obs = env.reset()
+        elif op == gio.OP_RESET_IDX:
+            obs = env.reset(t(idx))
+        elif op == gio.OP_STEP:
+            a = t(actions)
+            obs, rewards, dones = env.step(a.int() if step % 3 == 0 else a)     # int32 actions are accepted
+        else:
+            obs, rewards, dones = env.step_subset(t(actions[idx]), t(idx))
+        want_boards = gio.unpack(g["boards"][step], (2, m, n))
+        assert obs["observation"].dtype == torch.float32 and obs["action_mask"].dtype == torch.bool
+        assert rewards.dtype == torch.float32 and dones.dtype == torch.bool
+        assert np.array_equal(obs["observation"].cpu().numpy(), want_boards.astype(np.float32)), step
+        assert np.array_equal(obs["action_mask"].cpu().numpy(), gio.unpack(g["mask"][step], (m * n,))), step
+        assert np.array_equal(rewards.cpu().numpy(), g["rewards"][step]), step
+        assert np.array_equal(dones.cpu().numpy(), g["dones"][step]), step
+        if mirrors:
+            assert np.array_equal(held[0].cpu().numpy(), want_boards.astype(np.float32)), step
+            assert np.array_equal(held[1].cpu().numpy(), g["player"][step]), step
+            assert np.array_equal(held[2].cpu().numpy(), g["count"][step]), step
+    fresh = make_env(m, n, k, ne)     # state read back only at the end in packed mode
+    assert np.array_equal(env.current_player.cpu().numpy(), g["player"][-1])
+    assert np.array_equal(env.move_counts.cpu().numpy(), g["count"][-1])
+    assert fresh.boards.sum().item() == 0
+
+
+@pytest.mark.parametrize("path", gio.files("env_poke_"), ids=gio.name)
+def test_golden_env_poke(path):
+    """Positions written straight into env.boards / current_player / move_counts (as the reference's
+    tests do) and one step from there: every line direction, overlines, wraps, draws."""
+    g = gio.load(path)
+    m, n, k, ne = (int(x) for x in g["geom"])
+    env = make_env(m, n, k, ne)
+    env.reset()
+    env.boards[:] = t(gio.unpack(g["init_boards"], (2, m, n)).astype(np.float32))
+    env.current_player[:] = t(g["init_player"])
+    env.move_counts[:] = t(g["init_count"])
+    obs, rewards, dones = env.step(t(g["actions"]))
+    assert np.array_equal(env.boards.cpu().numpy().astype(bool), gio.unpack(g["boards"], (2, m, n)))
+    assert np.array_equal(obs["action_mask"].cpu().numpy(), gio.unpack(g["mask"], (m * n,)))
+    assert np.array_equal(env.current_player.cpu().numpy(), g["player"])
+    assert np.array_equal(env.move_counts.cpu().numpy(), g["count"])
+    assert np.array_equal(rewards.cpu().numpy(), g["rewards"])
+    assert np.array_equal(dones.cpu().numpy(), g["dones"])
+
+
+GEOMS = [(3, 3, 3, 1000), (9, 9, 5, 4099), (13, 13, 5, 1031), (19, 19, 5, 517), (15, 15, 5, 300),
+         (7, 11, 4, 777), (6, 7, 4, 640), (4, 31, 4, 65), (16, 31, 5, 33), (5, 5, 1, 64), (10, 10, 10, 129)]
+
+
+@pytest.mark.parametrize("m,n,k,ne", GEOMS, ids=lambda v: str(v))
+def test_oracle_parity_random_play(m, n, k, ne):
+    """Seeded random legal play with finished envs reset: CUDA env vs CPU oracle step by step, with
+    the actions drawn by mnk_random_legal and checked against the oracle's Philox contract."""
+    env = make_env(m, n, k, ne, env_offset=12345)
+    ref = orc.OracleEnv(m, n, k, ne)
+    obs = env.reset()
+    ref.reset()
+    steps = min(3 * m * n // 2 + 5, 220)
+    for step in range(steps):
+        a = env.random_legal_actions(seed=99, counter=step)
+        want = orc.random_legal_actions(obs["action_mask"].cpu().numpy(), 99, step, env_offset=12345)
+        assert np.array_equal(a.cpu().numpy(), want), step
+        if step % 2 == 0:
+            obs, r, d = env.step(a)
+            o2, r2, d2 = ref.step(want)
+            done_idx = np.nonzero(d2)[0]
+            if len(done_idx):
+                obs = env.reset(t(done_idx))
+                o2 = ref.reset(done_idx)
+        else:   # fused step + reset of finished envs; returned obs is the pre-reset one
+            obs, r, d = env.step_autoreset(a)
+            o2, r2, d2 = ref.step(want)
+            assert np.array_equal(obs["observation"].cpu().numpy(), o2["observation"]), step
+            done_idx = np.nonzero(d2)[0]
+            if len(done_idx):
+                o2 = ref.reset(done_idx)
+            obs = env.observe()
+        assert np.array_equal(r.cpu().numpy(), r2) and np.array_equal(d.cpu().numpy(), d2), step
+        assert np.array_equal(obs["observation"].cpu().numpy(), o2["observation"]), step
+        assert np.array_equal(obs["action_mask"].cpu().numpy(), o2["action_mask"]), step
+    assert np.array_equal(env.current_player.cpu().numpy(), ref.current_player)
+    assert np.array_equal(env.move_counts.cpu().numpy(), ref.move_counts)
+    assert np.array_equal(env.boards.cpu().numpy(), ref.boards.astype(np.float32))
+
+
+def test_baseline_size_properties_and_oracle():
+    """BASELINE cfg 2 size (9x9x5, 65,536 envs): oracle parity on a short run plus invariants that
+    hold for any number of envs under legal play."""
+    m, n, k, ne = 9, 9, 5, 65536
+    env = make_env(m, n, k, ne)
+    ref = orc.OracleEnv(m, n, k, ne)
+    env.reset()
+    ref.reset()
+    total_done = 0
+    for step in range(70):
+        a = env.random_legal_actions(seed=3, counter=step)
+        obs, r, d = env.step_autoreset(a)
+        _, r2, d2 = ref.step(a.cpu().numpy())
+        assert np.array_equal(r.cpu().numpy(), r2) and np.array_equal(d.cpu().numpy(), d2), step
+        o = obs["observation"]
+        stones = o.sum(dim=(1, 2, 3))
+        assert torch.equal(obs["action_mask"], ~(o[:, 0].bool() | o[:, 1].bool()).flatten(1))
+        assert bool((r <= d.float()).all())                 # a reward implies done
+        assert bool((o[:, 0] * o[:, 1]).sum() == 0)         # legal play never double-occupies
+        done_idx = np.nonzero(d2)[0]
+        total_done += len(done_idx)
+        if len(done_idx):
+            ref.reset(done_idx)
+        assert torch.equal(env.move_counts, torch.where(d, torch.zeros_like(stones), stones).long()), step
+    assert total_done > 1000
+    assert np.array_equal(env.boards.cpu().numpy(), ref.boards.astype(np.float32))
+
+
+def test_tail_tiles_and_empty_cases():
+    """num_envs not a multiple of the 32-env warp tile, single env, empty index lists."""
+    for ne in (1, 2, 31, 33, 63, 97):
+        env = make_env(9, 9, 5, ne)
+        ref = orc.OracleEnv(9, 9, 5, ne)
+        env.reset(), ref.reset()
+        for step in range(12):
+            a = env.random_legal_actions(1, step)
+            obs, r, d = env.step(a)
+            o2, r2, d2 = ref.step(a.cpu().numpy())
+            assert np.array_equal(obs["observation"].cpu().numpy(), o2["observation"])
+            assert np.array_equal(obs["action_mask"].cpu().numpy(), o2["action_mask"])
+    env = make_env(3, 3, 3, 8)
+    env.reset()
+    obs, r, d = env.step_subset(torch.empty(0, dtype=torch.long, device=DEV), torch.empty(0, dtype=torch.long, device=DEV))
+    assert r.sum().item() == 0 and not d.any() and obs["action_mask"].all()     # the reference raises here; we no-op
+    obs = env.reset(torch.empty(0, dtype=torch.long, device=DEV))
+    assert obs["observation"].shape == (8, 2, 3, 3)
+
+
+def test_reference_env_tests_port():
+    """The two env-level reference tests (src/tests/test_mnk_integration.py:50-81)."""
+    env = make_env(3, 3, 3, 1)
+    env.reset()
+    env.boards[0, 0, 0, 0] = 1
+    env.boards[0, 0, 0, 1] = 1
+    _, rewards, dones = env.step(torch.tensor([2], device=DEV))
+    assert dones[0].item() is True
+    assert rewards[0].item() == 1.0
+    # test_env_illegal_move: fails on the reference itself (validators are dead code, :86-104);
+    # the drop-in reproduces the silent behaviour by default and raises in strict mode.
+    env = make_env(3, 3, 3, 1)
+    env.reset()
+    env.boards[0, 0, 0, 0] = 1
+    obs, r, d = env.step(torch.tensor([0], device=DEV))
+    assert env.move_counts[0].item() == 1 and env.current_player[0].item() == 1 and not d[0].item()
+    strict = make_env(3, 3, 3, 1, strict=True)
+    strict.reset()
+    strict.boards[0, 0, 0, 0] = 1
+    with pytest.raises(ValueError, match="Illegal Move"):
+        strict.step(torch.tensor([0], device=DEV))
+    with pytest.raises(ValueError, match="Action out of bounds"):
+        strict.step(torch.tensor([9], device=DEV))
+
+
+def test_observe_returns_fresh_tensors_and_swap_fix():
+    env = make_env(3, 3, 3, 4)
+    env.reset()
+    a = env.observe()
+    b = env.observe()
+    assert a["observation"].data_ptr() != b["observation"].data_ptr()
+    a["observation"].fill_(7)         # callers mutate what observe() returns (wrapper :89,:106,:110)
+    assert env.observe()["observation"].sum().item() == 0
+    env.step(torch.tensor([0, 1, 2, 3], device=DEV))
+    swap = torch.tensor([0, 1, 0, 1], dtype=torch.uint8, device=DEV)
+    o = env._observe_packed(swap=swap)["observation"]
+    raw = env.observe()["observation"]
+    assert torch.equal(o[0], raw[0]) and torch.equal(o[1], raw[1].flip(0)) and torch.equal(o[3], raw[3].flip(0))
+
+
+def test_host_step_path():
+    env = make_env(9, 9, 5, 1000)
+    twin = make_env(9, 9, 5, 1000)
+    env.reset(), twin.reset()
+    host_a = torch.empty(1000, dtype=torch.long).pin_memory()
+    host_out = torch.empty(5000, dtype=torch.uint8).pin_memory()
+    for step in range(30):
+        a = twin.random_legal_actions(5, step)
+        host_a.copy_(a)
+        obs, r, d = env.step_host(host_a, host_out, autoreset=True)
+        o2, r2, d2 = twin.step_autoreset(a)
+        assert not r.is_cuda and torch.equal(r, r2.cpu()) and torch.equal(d, d2.cpu())
+        assert torch.equal(obs["observation"], o2["observation"])
+    assert env.state_checksum() == twin.state_checksum()

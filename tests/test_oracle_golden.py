@@ -171,21 +171,13 @@ def test_torch_port_env_trace(path):
         assert np.array_equal(rewards.numpy(), g["rewards"][t]) and np.array_equal(dones.numpy(), g["dones"][t]), t
 
 
-@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/src"), reason="reference not mounted (GPU box)")
+@pytest.mark.skipif(not __import__("ref_loader").available(), reason="reference not mounted (GPU box)")
 def test_oracle_live_against_reference_large_batch():
     """Where the reference is mounted (build container), run it live next to the C oracle on a
     larger batch than the committed fixtures hold."""
-    import sys
     import torch
-    sys.path.insert(0, "/root/reference/src")
-    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "env" or k.startswith("env.")}
-    try:
-        from env.torch_vector_mnk_env import TorchVectorMnkEnv as RefEnv
-    finally:
-        sys.path.remove("/root/reference/src")
-        for k in [k for k in sys.modules if k == "env" or k.startswith("env.")]:
-            del sys.modules[k]
-        sys.modules.update(saved)
+    import ref_loader
+    RefEnv = ref_loader.load("env.torch_vector_mnk_env").TorchVectorMnkEnv
     rng = np.random.default_rng(5)
     for (m, n, k) in [(9, 9, 5), (6, 7, 4)]:
         ne = 512
