@@ -138,7 +138,8 @@ class TorchVectorMnkEnv:
             self._call(self._L.mnk_reset, None, 0)
         else:
             idx = torch.as_tensor(env_indices, device=self._dev).to(torch.long).contiguous()
-            self._call(self._L.mnk_reset, _ptr(idx), idx.numel())
+            if idx.numel() > 0:     # an empty tensor has a NULL data_ptr, which the C ABI reads as "all envs"
+                self._call(self._L.mnk_reset, _ptr(idx), idx.numel())
         self._refresh_mirrors()
         return self._observe_packed()
 
@@ -188,6 +189,12 @@ class TorchVectorMnkEnv:
             obs, mask = out
         elif materialise:
             obs, mask = self._new_obs()
+        if idx is not None and idx.numel() == 0:
+            # the reference raises on an empty subset (view(0, -1) in _check_wins); here it is a no-op
+            rewards.zero_(), dones.zero_()
+            if obs is not None or mask is not None:
+                self._call(self._L.mnk_observe, _ptr(obs), _ptr(mask), None, 0)
+            return {"observation": obs, "action_mask": mask}, rewards, dones
         self._call(self._L.mnk_step, _ptr(a), _ptr(idx), a.numel(), _ptr(rewards), _ptr(dones), _ptr(obs), _ptr(mask),
                    None, flags)
         self._refresh_mirrors()
