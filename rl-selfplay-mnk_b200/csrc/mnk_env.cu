@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kTileThreads)
 step_dense_kernel(G g, mnk_state_t st, const void* __restrict__ actions, float* __restrict__ rewards,
                   u8* __restrict__ dones, float* __restrict__ obs, u8* __restrict__ mask,
                   int32_t* __restrict__ illegal, u32 flags) {
+    __shared__ u32 tile_smem[kTileWarps * TileStream<G>::kWords];
     const int lane = threadIdx.x & 31;
     const long long tile = (long long)blockIdx.x * kTileWarps + (threadIdx.x >> 5);
     const long long e0 = tile * kTileEnvs;
@@ -62,7 +63,8 @@ step_dense_kernel(G g, mnk_state_t st, const void* __restrict__ actions, float* 
         if ((flags & MNK_STEP_AUTORESET) && r.done) env_zero(s);
         env_store(st, e, s);
     }
-    if (obs != nullptr || mask != nullptr) emit_tile(g, e0, tile_envs, lane, obsd, legd, obs, mask);
+    if (obs != nullptr || mask != nullptr)
+        emit_tile_auto(g, tile_smem + (threadIdx.x >> 5) * TileStream<G>::kWords, e0, tile_envs, lane, obsd, legd, obs, mask);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -96,6 +98,7 @@ template <class G>
 __global__ void __launch_bounds__(kTileThreads)
 observe_kernel(G g, mnk_state_t st, float* __restrict__ obs, u8* __restrict__ mask,
                const u8* __restrict__ swap, int fix_all_masked) {
+    __shared__ u32 tile_smem[kTileWarps * TileStream<G>::kWords];
     const int lane = threadIdx.x & 31;
     const long long tile = (long long)blockIdx.x * kTileWarps + (threadIdx.x >> 5);
     const long long e0 = tile * kTileEnvs;
@@ -112,7 +115,7 @@ observe_kernel(G g, mnk_state_t st, float* __restrict__ obs, u8* __restrict__ ma
     u64 obsd[G::NWD];
     u64 legd[G::NWL];
     build_views(g, s, sw, fix_all_masked != 0, obsd, legd);
-    emit_tile(g, e0, tile_envs, lane, obsd, legd, obs, mask);
+    emit_tile_auto(g, tile_smem + (threadIdx.x >> 5) * TileStream<G>::kWords, e0, tile_envs, lane, obsd, legd, obs, mask);
 }
 
 // ------------------------------------------------------------------------------------------------
