@@ -371,13 +371,17 @@ MNK_DEV void emit_tile(const G& g, long long e0, int tile_envs, int lane, const 
 // Stream materialisation (static geometries, full 32-env tiles, 16-byte aligned outputs).
 //
 // A tile of 32 envs is 32*OB observation bits (OB = 2*cells) = exactly OB 32-bit words, and
-// 32*cells mask bits = exactly `cells` words.  The warp first stages every env's dense vectors in
-// shared memory (one odd-strided row per lane), then gathers them into the two contiguous tile
-// bitstreams, and finally expands the streams with 128-bit stores: one nibble -> one float4 of
-// the f32 observation (512 contiguous bytes per warp store), one half-word -> 16 mask bytes.
-// Compared with emit_tile this costs ~5x fewer instructions per output byte and uses the widest
-// store the LSU has; emit_tile remains the path for tail tiles and runtime geometries.
+// 32*cells mask bits = exactly `cells` words.  The CTA's compute warp (lane L owns env e0+L) stages
+// every env's dense vectors in shared memory (one odd-strided row per lane); then ALL kStreamThreads
+// threads of the CTA gather the rows into the two contiguous tile bitstreams and expand them with
+// 128-bit stores: one nibble -> one float4 of the f32 observation (512 contiguous bytes per warp
+// store), one half-word -> 16 mask bytes.  Spreading the expansion -- 84% of the kernel's
+// instructions -- over 4 warps per tile keeps ~55 warps per SM resident at cfg2 (one warp per tile
+// left the SM schedulers idle 2/3 of the time: ncu, profiles/).  emit_tile (warp shuffles, narrow
+// stores) remains the path for tail tiles, unaligned outputs and runtime geometries.
 // ------------------------------------------------------------------------------------------------
+constexpr int kStreamThreads = 128;
+
 template <class G>
 struct TileStream {   // runtime geometries: unused
     static constexpr int kWords = 1;
@@ -399,116 +403,116 @@ struct TileStream<SGeom<M, N, K>> {
     static constexpr int kWords = kStreamL + LB;
 };
 
-// gather `bits_per_env`-bit rows (staged at `stage`, row stride `stride` words, zero pad word after
-// each row) into the contiguous tile bitstream `stream` of `bits_per_env` words
+// one 32-bit word of the contiguous tile bitstream, gathered from BITS-bit rows staged at `stage`
+// (row stride STRIDE words, a zero pad word after each row)
 template <int BITS, int STRIDE>
-MNK_DEV void gather_stream(const u32* stage, u32* stream, int lane) {
-#pragma unroll
-    for (int r = 0; r < (BITS + 31) / 32; ++r) {
-        const int w = lane + 32 * r;
-        if (w < BITS) {
-            const int bitpos = 32 * w;
-            const int t = bitpos / BITS;
-            const int o = bitpos - t * BITS;
-            const u32* row = stage + t * STRIDE;
-            u32 v;
-            if constexpr (BITS >= 32) {
-                v = __funnelshift_r(row[o >> 5], row[(o >> 5) + 1], o & 31);
-                const int rem = BITS - o;
-                if (rem < 32) v = (v & ((1u << rem) - 1u)) | (row[STRIDE] << rem);   // spill into env t+1
-            } else {   // tiny boards: a 32-bit window spans several single-word rows
-                v = 0u;
-                int filled = 0, tt = t, oo = o;
-                while (filled < 32 && tt < 32) {
-                    const int take = min(BITS - oo, 32 - filled);
-                    v |= ((stage[tt * STRIDE] >> oo) & ((1u << take) - 1u)) << filled;
-                    filled += take;
-                    ++tt;
-                    oo = 0;
-                }
-            }
-            stream[w] = v;
+MNK_DEV u32 gather_stream_word(const u32* stage, int w) {
+    const int bitpos = 32 * w;
+    const int t = bitpos / BITS;
+    const int o = bitpos - t * BITS;
+    const u32* row = stage + t * STRIDE;
+    u32 v;
+    if constexpr (BITS >= 32) {
+        v = __funnelshift_r(row[o >> 5], row[(o >> 5) + 1], o & 31);
+        const int rem = BITS - o;
+        if (rem < 32) v = (v & ((1u << rem) - 1u)) | (row[STRIDE] << rem);   // spill into env t+1
+    } else {   // tiny boards: a 32-bit window spans several single-word rows
+        v = 0u;
+        int filled = 0, tt = t, oo = o;
+        while (filled < 32 && tt < 32) {
+            const int take = min(BITS - oo, 32 - filled);
+            v |= ((stage[tt * STRIDE] >> oo) & ((1u << take) - 1u)) << filled;
+            filled += take;
+            ++tt;
+            oo = 0;
         }
     }
+    return v;
 }
 
+// Called by all kStreamThreads threads of the CTA; obsd / legd are read from warp 0 only.
 template <int M, int N, int K>
-MNK_DEV void emit_tile_stream(const SGeom<M, N, K>&, u32* smem, long long e0, int lane,
-                              const u64 (&obsd)[SGeom<M, N, K>::NWD], const u64 (&legd)[SGeom<M, N, K>::NWL],
-                              float* __restrict__ obs, u8* __restrict__ mask) {
+MNK_DEV void emit_block_stream(const SGeom<M, N, K>&, u32* smem, long long e0, const u64 (&obsd)[SGeom<M, N, K>::NWD],
+                               const u64 (&legd)[SGeom<M, N, K>::NWL], float* __restrict__ obs,
+                               u8* __restrict__ mask) {
     using TS = TileStream<SGeom<M, N, K>>;
-    // 1. stage this lane's env
-    if (obs != nullptr) {
-        u32* row = smem + TS::kStageO + lane * TS::OSTRIDE;
+    const int tid = threadIdx.x;
+    // 1. the compute warp stages its 32 envs
+    if (tid < 32) {
+        if (obs != nullptr) {
+            u32* row = smem + TS::kStageO + tid * TS::OSTRIDE;
 #pragma unroll
-        for (int j = 0; j < TS::OW; ++j) row[j] = (j & 1) ? (u32)(obsd[j >> 1] >> 32) : (u32)obsd[j >> 1];
-        row[TS::OW] = 0u;
-    }
-    if (mask != nullptr) {
-        u32* row = smem + TS::kStageL + lane * TS::LSTRIDE;
+            for (int j = 0; j < TS::OW; ++j) row[j] = (j & 1) ? (u32)(obsd[j >> 1] >> 32) : (u32)obsd[j >> 1];
+            row[TS::OW] = 0u;
+        }
+        if (mask != nullptr) {
+            u32* row = smem + TS::kStageL + tid * TS::LSTRIDE;
 #pragma unroll
-        for (int j = 0; j < TS::LW; ++j) row[j] = (j & 1) ? (u32)(legd[j >> 1] >> 32) : (u32)legd[j >> 1];
-        row[TS::LW] = 0u;
+            for (int j = 0; j < TS::LW; ++j) row[j] = (j & 1) ? (u32)(legd[j >> 1] >> 32) : (u32)legd[j >> 1];
+            row[TS::LW] = 0u;
+        }
     }
-    __syncwarp();
+    __syncthreads();
     // 2. tile bitstreams
-    if (obs != nullptr) gather_stream<TS::OB, TS::OSTRIDE>(smem + TS::kStageO, smem + TS::kStreamO, lane);
-    if (mask != nullptr) gather_stream<TS::LB, TS::LSTRIDE>(smem + TS::kStageL, smem + TS::kStreamL, lane);
-    __syncwarp();
+    if (obs != nullptr)
+        for (int w = tid; w < TS::OB; w += kStreamThreads)
+            smem[TS::kStreamO + w] = gather_stream_word<TS::OB, TS::OSTRIDE>(smem + TS::kStageO, w);
+    if (mask != nullptr)
+        for (int w = tid; w < TS::LB; w += kStreamThreads)
+            smem[TS::kStreamL + w] = gather_stream_word<TS::LB, TS::LSTRIDE>(smem + TS::kStageL, w);
+    __syncthreads();
     // 3. expand
     if (obs != nullptr) {
         float4* dst = reinterpret_cast<float4*>(obs + (size_t)e0 * TS::OB);
         const u32* stream = smem + TS::kStreamO;
-        const int shift = 4 * (lane & 7);
+        const int shift = 4 * (tid & 7);
         constexpr int Q = 8 * TS::OB;                 // float4 per tile
 #pragma unroll 4
-        for (int j = 0; j < (Q + 31) / 32; ++j) {
-            const int q = lane + 32 * j;
-            if (q < Q) {
-                const u32 nib = stream[q >> 3] >> shift;
-                float4 f;
-                f.x = __uint_as_float((nib & 1u) * 0x3f800000u);
-                f.y = __uint_as_float((nib & 2u) * 0x1fc00000u);
-                f.z = __uint_as_float((nib & 4u) * 0x0fe00000u);
-                f.w = __uint_as_float((nib & 8u) * 0x07f00000u);
-                __stcs(dst + q, f);
-            }
+        for (int q = tid; q < Q; q += kStreamThreads) {
+            const u32 nib = stream[q >> 3] >> shift;
+            float4 f;
+            f.x = __uint_as_float((nib & 1u) * 0x3f800000u);
+            f.y = __uint_as_float((nib & 2u) * 0x1fc00000u);
+            f.z = __uint_as_float((nib & 4u) * 0x0fe00000u);
+            f.w = __uint_as_float((nib & 8u) * 0x07f00000u);
+            __stcs(dst + q, f);
         }
     }
     if (mask != nullptr) {
         uint4* dst = reinterpret_cast<uint4*>(mask + (size_t)e0 * TS::LB);
         const u32* stream = smem + TS::kStreamL;
-        const int shift = 16 * (lane & 1);
+        const int shift = 16 * (tid & 1);
         constexpr int Q = 2 * TS::LB;                 // 16-byte groups per tile
-#pragma unroll 2
-        for (int j = 0; j < (Q + 31) / 32; ++j) {
-            const int q = lane + 32 * j;
-            if (q < Q) {
-                const u32 h = stream[q >> 1] >> shift;
-                uint4 b;
-                b.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
-                b.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
-                b.z = (((h >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
-                b.w = (((h >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
-                __stcs(dst + q, b);
-            }
+        for (int q = tid; q < Q; q += kStreamThreads) {
+            const u32 h = stream[q >> 1] >> shift;
+            uint4 b;
+            b.x = ((h & 0xFu) * 0x00204081u) & 0x01010101u;
+            b.y = (((h >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+            b.z = (((h >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+            b.w = (((h >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+            __stcs(dst + q, b);
         }
     }
-    __syncwarp();   // the staging rows are reused by the caller's next tile, if any
 }
 
-// picks the stream path when its preconditions hold (warp-uniform), else the shuffle path
+// Tile kernels run one CTA per 32-env tile: kStreamThreads threads for static geometries (warp 0
+// computes, all warps materialise), a single warp for runtime geometries.
 template <class G>
-MNK_DEV void emit_tile_auto(const G& g, u32* smem, long long e0, int tile_envs, int lane, const u64 (&obsd)[G::NWD],
-                            const u64 (&legd)[G::NWL], float* __restrict__ obs, u8* __restrict__ mask) {
-    if constexpr (G::kStatic) {
-        const bool aligned = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
-        if (tile_envs == 32 && aligned) {
-            emit_tile_stream(g, smem, e0, lane, obsd, legd, obs, mask);
-            return;
-        }
-    }
-    emit_tile(g, e0, tile_envs, lane, obsd, legd, obs, mask);
+constexpr int tile_cta_threads() { return G::kStatic ? kStreamThreads : 32; }
+
+// block-uniform: can this tile take the stream path?
+template <class G>
+MNK_DEV bool tile_streams(int tile_envs, const float* obs, const u8* mask) {
+    if constexpr (G::kStatic)
+        return tile_envs == 32 && ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
+    else
+        return false;
+}
+
+template <class G>
+MNK_DEV void emit_block_stream_any(const G& g, u32* smem, long long e0, const u64 (&obsd)[G::NWD],
+                                   const u64 (&legd)[G::NWL], float* __restrict__ obs, u8* __restrict__ mask) {
+    if constexpr (G::kStatic) emit_block_stream(g, smem, e0, obsd, legd, obs, mask);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -49,7 +49,7 @@ static inline int mnk_launch_status() {
     return e == cudaSuccess ? MNK_OK : (int)e;
 }
 
-// warp-tile kernels: one warp per 32 consecutive envs, 4 warps per CTA
+// warp-tile kernels (pack): one warp per 32 consecutive envs, 4 warps per CTA
 constexpr int kTileEnvs = 32;
 constexpr int kTileWarps = 4;
 constexpr int kTileThreads = kTileWarps * 32;
@@ -57,6 +57,8 @@ static inline unsigned mnk_tile_blocks(long long num_envs) {
     const long long tiles = (num_envs + kTileEnvs - 1) / kTileEnvs;
     return (unsigned)((tiles + kTileWarps - 1) / kTileWarps);
 }
+// CTA-per-tile kernels (step_dense, observe): one CTA per 32 consecutive envs
+static inline unsigned mnk_cta_tiles(long long num_envs) { return (unsigned)((num_envs + kTileEnvs - 1) / kTileEnvs); }
 // thread-per-env kernels
 constexpr int kFlatThreads = 256;
 static inline unsigned mnk_flat_blocks(long long count) { return (unsigned)((count + kFlatThreads - 1) / kFlatThreads); }

@@ -34,37 +34,37 @@ reset_kernel(mnk_state_t st, const int64_t* __restrict__ idx, long long count) {
 // dense step (+ optional observation / mask materialisation, auto-reset, strict accounting)
 // ------------------------------------------------------------------------------------------------
 template <class G, bool ACT32>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(tile_cta_threads<G>())
 step_dense_kernel(G g, mnk_state_t st, const void* __restrict__ actions, float* __restrict__ rewards,
                   u8* __restrict__ dones, float* __restrict__ obs, u8* __restrict__ mask,
                   int32_t* __restrict__ illegal, u32 flags) {
-    __shared__ u32 tile_smem[kTileWarps * TileStream<G>::kWords];
+    __shared__ u32 tile_smem[TileStream<G>::kWords];
     const int lane = threadIdx.x & 31;
-    const long long tile = (long long)blockIdx.x * kTileWarps + (threadIdx.x >> 5);
-    const long long e0 = tile * kTileEnvs;
-    if (e0 >= st.num_envs) return;   // warp-uniform
-    const long long e = e0 + lane;
-    const bool live = e < st.num_envs;
+    const long long e0 = (long long)blockIdx.x * kTileEnvs;
     const int tile_envs = (int)min((long long)kTileEnvs, st.num_envs - e0);
-
-    EnvRegs<G> s;
-    env_zero(s);
+    const bool emit = obs != nullptr || mask != nullptr;
+    const bool stream = emit && tile_streams<G>(tile_envs, obs, mask);   // block-uniform
     u64 obsd[G::NWD];
     u64 legd[G::NWL];
-    if (live) {
-        env_load(st, e, s);
-        const long long a = ACT32 ? (long long)static_cast<const int32_t*>(actions)[e]
-                                  : (long long)static_cast<const int64_t*>(actions)[e];
-        const MoveResult r = apply_move(g, s, a);
-        rewards[e] = r.reward;
-        dones[e] = r.done ? 1 : 0;
-        if (illegal != nullptr && r.illegal) note_illegal(illegal, e);
-        if (obs != nullptr || mask != nullptr) build_views(g, s, false, false, obsd, legd);
-        if ((flags & MNK_STEP_AUTORESET) && r.done) env_zero(s);
-        env_store(st, e, s);
+    if (threadIdx.x < 32) {   // the compute warp: lane L owns env e0 + L
+        const long long e = e0 + lane;
+        EnvRegs<G> s;
+        env_zero(s);
+        if (e < st.num_envs) {
+            env_load(st, e, s);
+            const long long a = ACT32 ? (long long)static_cast<const int32_t*>(actions)[e]
+                                      : (long long)static_cast<const int64_t*>(actions)[e];
+            const MoveResult r = apply_move(g, s, a);
+            rewards[e] = r.reward;
+            dones[e] = r.done ? 1 : 0;
+            if (illegal != nullptr && r.illegal) note_illegal(illegal, e);
+            if (emit) build_views(g, s, false, false, obsd, legd);
+            if ((flags & MNK_STEP_AUTORESET) && r.done) env_zero(s);
+            env_store(st, e, s);
+        }
+        if (emit && !stream) emit_tile(g, e0, tile_envs, lane, obsd, legd, obs, mask);
     }
-    if (obs != nullptr || mask != nullptr)
-        emit_tile_auto(g, tile_smem + (threadIdx.x >> 5) * TileStream<G>::kWords, e0, tile_envs, lane, obsd, legd, obs, mask);
+    if (stream) emit_block_stream_any(g, tile_smem, e0, obsd, legd, obs, mask);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -95,27 +95,29 @@ step_subset_kernel(G g, mnk_state_t st, const void* __restrict__ actions, const 
 // observe / unpack
 // ------------------------------------------------------------------------------------------------
 template <class G>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(tile_cta_threads<G>())
 observe_kernel(G g, mnk_state_t st, float* __restrict__ obs, u8* __restrict__ mask,
                const u8* __restrict__ swap, int fix_all_masked) {
-    __shared__ u32 tile_smem[kTileWarps * TileStream<G>::kWords];
+    __shared__ u32 tile_smem[TileStream<G>::kWords];
     const int lane = threadIdx.x & 31;
-    const long long tile = (long long)blockIdx.x * kTileWarps + (threadIdx.x >> 5);
-    const long long e0 = tile * kTileEnvs;
-    if (e0 >= st.num_envs) return;
-    const long long e = e0 + lane;
+    const long long e0 = (long long)blockIdx.x * kTileEnvs;
     const int tile_envs = (int)min((long long)kTileEnvs, st.num_envs - e0);
-    EnvRegs<G> s;
-    env_zero(s);
-    bool sw = false;
-    if (e < st.num_envs) {
-        env_load(st, e, s);
-        sw = swap != nullptr && swap[e] != 0;
-    }
+    const bool stream = tile_streams<G>(tile_envs, obs, mask);   // block-uniform
     u64 obsd[G::NWD];
     u64 legd[G::NWL];
-    build_views(g, s, sw, fix_all_masked != 0, obsd, legd);
-    emit_tile_auto(g, tile_smem + (threadIdx.x >> 5) * TileStream<G>::kWords, e0, tile_envs, lane, obsd, legd, obs, mask);
+    if (threadIdx.x < 32) {
+        const long long e = e0 + lane;
+        EnvRegs<G> s;
+        env_zero(s);
+        bool sw = false;
+        if (e < st.num_envs) {
+            env_load(st, e, s);
+            sw = swap != nullptr && swap[e] != 0;
+        }
+        build_views(g, s, sw, fix_all_masked != 0, obsd, legd);
+        if (!stream) emit_tile(g, e0, tile_envs, lane, obsd, legd, obs, mask);
+    }
+    if (stream) emit_block_stream_any(g, tile_smem, e0, obsd, legd, obs, mask);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -235,7 +237,7 @@ int mnk_observe(const mnk_state_t* st, float* obs, uint8_t* mask, const uint8_t*
     if (st->num_envs == 0) return MNK_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return mnk_dispatch_geom(*st, [&](auto g) {
-        observe_kernel<<<mnk_tile_blocks(st->num_envs), kTileThreads, 0, s>>>(g, *st, obs, mask, swap, fix_all_masked);
+        observe_kernel<<<mnk_cta_tiles(st->num_envs), tile_cta_threads<decltype(g)>(), 0, s>>>(g, *st, obs, mask, swap, fix_all_masked);
         return mnk_launch_status();
     });
 }
@@ -268,11 +270,13 @@ int mnk_step(const mnk_state_t* st, const void* actions, const int64_t* idx, int
     if (idx == nullptr) {
         return mnk_dispatch_geom(*st, [&](auto g) {
             using G = decltype(g);
-            const unsigned blocks = mnk_tile_blocks(st->num_envs);
+            const unsigned blocks = mnk_cta_tiles(st->num_envs);
+            // no materialisation => only the compute warp has work: launch single-warp CTAs
+            const int threads = (obs != nullptr || mask != nullptr) ? tile_cta_threads<G>() : 32;
             if (act32)
-                step_dense_kernel<G, true><<<blocks, kTileThreads, 0, s>>>(g, *st, actions, rewards, dones, obs, mask, illegal, flags);
+                step_dense_kernel<G, true><<<blocks, threads, 0, s>>>(g, *st, actions, rewards, dones, obs, mask, illegal, flags);
             else
-                step_dense_kernel<G, false><<<blocks, kTileThreads, 0, s>>>(g, *st, actions, rewards, dones, obs, mask, illegal, flags);
+                step_dense_kernel<G, false><<<blocks, threads, 0, s>>>(g, *st, actions, rewards, dones, obs, mask, illegal, flags);
             return mnk_launch_status();
         });
     }
