@@ -124,6 +124,60 @@ int mnk_import_meta(const mnk_state_t* st, const int64_t* current_player, const 
 int mnk_random_legal(const mnk_state_t* st, uint64_t seed, uint64_t counter, int64_t env_offset,
                      int deterministic, int64_t* actions, void* stream);
 
+/* Categorical(logits=masked logits) of the policy heads (src/alg/architectures/resnet.py:84-94)
+ * and its use in NNPolicy.act (policy.py:46-52) / PPOAgent.learn (src/alg/ppo.py:97-100):
+ * illegal logits -> -inf, an all-masked row -> all zeros (uniform), sample ~ softmax,
+ * log_prob(a) = logit_a - logsumexp, entropy = -sum p log p.  One warp per row.
+ *   logits       f32[rows][row_stride] (row_stride >= num_actions, in elements), num_actions <= 512
+ *   mask         u8[rows][num_actions] or NULL (everything legal)
+ *   given        NULL => draw the action (Gumbel-max on Philox(seed; row_offset + row, counter)),
+ *                deterministic != 0 => argmax, first index on ties (policy.py:49-50);
+ *                else i64[rows]: evaluate these actions instead of sampling
+ *   actions      i64[rows] out (may be NULL when `given` is set)
+ *   log_probs    f32[rows] or NULL, entropy f32[rows] or NULL */
+int mnk_masked_sample(const float* logits, int64_t row_stride, const uint8_t* mask, int32_t num_actions,
+                      int64_t rows, uint64_t seed, uint64_t counter, int64_t row_offset, int deterministic,
+                      const int64_t* given, int64_t* actions, float* log_probs, float* entropy, void* stream);
+
+/* ---- self-play wrapper: src/selfplay/torch_self_play_wrapper.py ------------------------------ */
+
+typedef struct mnk_selfplay {
+    uint8_t* agent_side;  /* u8[num_envs]  0 = agent plays black, 1 = white (wrapper.agent_side, :13)     */
+    uint8_t* pending;     /* u8[num_envs]  envs to reset at the next step (wrapper.pending_resets, :14)   */
+    uint32_t* episodes;   /* u32[num_envs] episodes started per env: the Philox counter of the side draw   */
+    uint64_t seed;        /* key of the side / opponent draws                                             */
+    int64_t env_offset;   /* global id of local env 0 (draws do not depend on the sharding)               */
+} mnk_selfplay_t;
+
+#define MNK_SP_ACTIONS_I32 1u        /* agent / opponent actions are int32_t[]                              */
+#define MNK_SP_RESET_ALL 2u          /* treat every env as pending: this is wrapper.reset() (:19-30)        */
+#define MNK_SP_DETERMINISTIC_OPP 4u  /* fused random opponent plays the first empty cell (policy.py:26-27)  */
+
+/* First half of TorchSelfPlayWrapper.step (:32-56).  Envs with pending[e] are reset, get a new side
+ * (forced_sides[e] if non-NULL, else the low Philox bit keyed by (seed, env_offset+e, ++episodes[e]))
+ * and ignore their action; every other env plays actions[e].  Outputs the agent ply's
+ * rewards f32 / terminated u8 and opp_active u8 (0 = opponent idle, 1 = opponent answers,
+ * 2 = opponent opens a freshly reset game: its result is discarded, :46).  If opp_obs / opp_mask
+ * are given they receive the view the reference hands to opponent_policy.act for EVERY env
+ * (channels swapped where the side to move is white, raw legal mask, :83-94); rows with
+ * opp_active == 0 are ignored by the second half. */
+int mnk_selfplay_agent(const mnk_state_t* st, const mnk_selfplay_t* sp, const void* actions,
+                       const int64_t* forced_sides, float* rewards, uint8_t* terminated, uint8_t* opp_active,
+                       float* opp_obs, uint8_t* opp_mask, uint32_t flags, void* stream);
+
+/* Second half (:58-67, :99-112): applies opp_actions where opp_active, reward -= r_opp and
+ * terminated = done_opp where opp_active == 1, pending = terminated, and writes the agent's
+ * canonical observation (planes swapped for a white agent) and mask (all-masked rows get cell 0). */
+int mnk_selfplay_opponent(const mnk_state_t* st, const mnk_selfplay_t* sp, const void* opp_actions,
+                          const uint8_t* opp_active, float* rewards, uint8_t* terminated, float* obs, uint8_t* mask,
+                          uint32_t flags, void* stream);
+
+/* Both halves in ONE launch for a RandomPolicy opponent (policy.py:13-29): the opponent's cell is
+ * drawn from the bitboards with Philox(seed; env_offset+e, step_counter). */
+int mnk_selfplay_step_random(const mnk_state_t* st, const mnk_selfplay_t* sp, const void* actions,
+                             const int64_t* forced_sides, uint64_t step_counter, float* rewards, uint8_t* terminated,
+                             float* obs, uint8_t* mask, uint32_t flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

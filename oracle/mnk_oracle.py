@@ -177,6 +177,7 @@ class OracleWrapper:
         if not opp_turn.any():
             return None, None
         active = env_idxs[opp_turn]
+        self.last_active = active          # test hook: which envs the opponent is answering
         full = self.env.observe()
         obs_subset = full["observation"][active].copy()
         mask_subset = full["action_mask"][active].copy()
@@ -227,7 +228,7 @@ def first_legal(mask: np.ndarray) -> np.ndarray:
 # ----------------------------------------------------------------------------
 _M0, _M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 _W0, _W1 = 0x9E3779B9, 0xBB67AE85
-STREAM_ACTION, STREAM_SIDE, STREAM_SAMPLE = 0, 1, 2
+STREAM_ACTION, STREAM_SIDE, STREAM_SAMPLE, STREAM_OPPONENT = 0, 1, 2, 3
 
 
 def philox4x32(c0, c1, c2, c3, k0: int, k1: int, rounds: int = 10):
@@ -256,13 +257,16 @@ def _draw_u32(seed: int, global_env_ids: np.ndarray, counter, stream: int) -> np
     return out[0]
 
 
-def random_legal_actions(mask: np.ndarray, seed: int, counter: int, env_offset: int = 0) -> np.ndarray:
-    """Contract of mnk_random_legal: j = mulhi32(philox, #legal); pick the j-th legal cell in
-    ascending cell order; rows with no legal cell draw uniformly from all cells (the
-    reference's RandomPolicy adds 1e-8 to every entry of such rows, policy.py:21-24)."""
+def random_legal_actions(mask: np.ndarray, seed: int, counter: int, env_offset: int = 0, env_ids=None,
+                         stream: int = STREAM_ACTION) -> np.ndarray:
+    """Contract of mnk_random_legal / the fused random opponent: j = mulhi32(philox, #legal); pick the
+    j-th legal cell in ascending cell order; rows with no legal cell draw uniformly from all cells
+    (the reference's RandomPolicy adds 1e-8 to every entry of such rows, policy.py:21-24).
+    Row i belongs to global env  env_offset + (env_ids[i] if given else i)."""
     mask = mask.astype(bool)
     n_env, cells = mask.shape
-    x = _draw_u32(seed, env_offset + np.arange(n_env), counter, STREAM_ACTION).astype(np.uint64)
+    ids = np.arange(n_env) if env_ids is None else np.asarray(env_ids)
+    x = _draw_u32(seed, env_offset + ids, counter, stream).astype(np.uint64)
     cnt = mask.sum(axis=1).astype(np.uint64)
     eff = np.where(cnt == 0, np.uint64(cells), cnt)
     j = ((x * eff) >> np.uint64(32)).astype(np.int64)

@@ -521,6 +521,7 @@ MNK_DEV void emit_block_stream_any(const G& g, u32* smem, long long e0, const u6
 #define MNK_STREAM_ACTION 0u
 #define MNK_STREAM_SIDE 1u
 #define MNK_STREAM_SAMPLE 2u
+#define MNK_STREAM_OPPONENT 3u
 
 MNK_DEV uint4 philox4x32_10(uint4 c, u32 k0, u32 k1) {
 #pragma unroll

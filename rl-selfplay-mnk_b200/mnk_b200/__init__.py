@@ -7,5 +7,9 @@ and ``selfplay/`` re-export these classes under the reference's module paths so 
 """
 from ._lib import build, lib, LIB_PATH  # noqa: F401
 from .env import TorchVectorMnkEnv  # noqa: F401
+from .policy import NNPolicy, Policy, RandomPolicy  # noqa: F401
+from .sampling import MaskedCategorical, masked_sample  # noqa: F401
+from .wrapper import TorchSelfPlayWrapper  # noqa: F401
 
-__all__ = ["build", "lib", "LIB_PATH", "TorchVectorMnkEnv"]
+__all__ = ["build", "lib", "LIB_PATH", "TorchVectorMnkEnv", "TorchSelfPlayWrapper", "Policy", "RandomPolicy", "NNPolicy",
+           "MaskedCategorical", "masked_sample"]

@@ -32,6 +32,15 @@ class MnkState(ctypes.Structure):
                 ("num_envs", ctypes.c_int64), ("bits", ctypes.c_void_p), ("meta", ctypes.c_void_p)]
 
 
+class MnkSelfplay(ctypes.Structure):
+    """struct mnk_selfplay of include/mnk_b200.h."""
+    _fields_ = [("agent_side", ctypes.c_void_p), ("pending", ctypes.c_void_p), ("episodes", ctypes.c_void_p),
+                ("seed", ctypes.c_uint64), ("env_offset", ctypes.c_int64)]
+
+
+SP_ACTIONS_I32, SP_RESET_ALL, SP_DETERMINISTIC_OPP = 1, 2, 4
+
+
 def sources():
     return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith(".cu"))
 
@@ -73,6 +82,7 @@ _lib: Optional[ctypes.CDLL] = None
 
 _VP, _I32, _I64, _U32, _U64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32, ctypes.c_uint64
 _ST = ctypes.POINTER(MnkState)
+_SP = ctypes.POINTER(MnkSelfplay)
 
 # name -> (restype, argtypes); must list every symbol include/mnk_b200.h declares
 SIGNATURES = {
@@ -88,6 +98,10 @@ SIGNATURES = {
     "mnk_export_meta": (_I32, [_ST, _VP, _VP, _VP]),
     "mnk_import_meta": (_I32, [_ST, _VP, _VP, _VP]),
     "mnk_random_legal": (_I32, [_ST, _U64, _U64, _I64, _I32, _VP, _VP]),
+    "mnk_masked_sample": (_I32, [_VP, _I64, _VP, _I32, _I64, _U64, _U64, _I64, _I32, _VP, _VP, _VP, _VP, _VP]),
+    "mnk_selfplay_agent": (_I32, [_ST, _SP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
+    "mnk_selfplay_opponent": (_I32, [_ST, _SP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
+    "mnk_selfplay_step_random": (_I32, [_ST, _SP, _VP, _VP, _U64, _VP, _VP, _VP, _VP, _U32, _VP]),
 }
 
 
