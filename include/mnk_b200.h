@@ -178,6 +178,31 @@ int mnk_selfplay_step_random(const mnk_state_t* st, const mnk_selfplay_t* sp, co
                              const int64_t* forced_sides, uint64_t step_counter, float* rewards, uint8_t* terminated,
                              float* obs, uint8_t* mask, uint32_t flags, void* stream);
 
+/* ---- rollout storage: src/alg/rollout_buffer.py, src/alg/ppo.py:78-133 ------------------------- */
+
+/* RolloutBuffer.add, observation + mask part (rollout_buffer.py:51,57): stores the agent's canonical
+ * planes of the CURRENT state (own stones first; agent_side as in mnk_selfplay_t, NULL = raw) into
+ * one packed slot  u64[2][words][num_envs]  -- 32 B per env at 9x9 instead of 729 B. */
+int mnk_rollout_store_obs(const mnk_state_t* st, const uint8_t* agent_side, uint64_t* slot, void* stream);
+
+/* RolloutBuffer.get_data_loader's b_obs[batch_idx], b_masks[batch_idx] (:101-110): materialises
+ * samples index[i] (NULL = 0..count-1) of the flattened [steps * num_envs] packed rollout
+ * (packed = u64[steps][2][words][num_envs]) as f32[count][2][m][n] and u8[count][m*n]
+ * (all-masked rows get cell 0, as the wrapper's canonical mask). */
+int mnk_rollout_gather(int32_t m, int32_t n, int32_t k, const uint64_t* packed, int64_t num_envs, const int64_t* index,
+                       int64_t count, float* obs, uint8_t* mask, void* stream);
+
+/* RolloutBuffer.compute_advantages_and_returns (:60-80): GAE(lambda) over [steps][num_envs] arrays,
+ * bit-identical in fp32 to the reference's tensor expressions. */
+int mnk_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int64_t steps,
+            int64_t num_envs, float gamma, float gae_lambda, float* advantages, float* returns, void* stream);
+
+/* PPOAgent.learn's episode accounting (ppo.py:110-120) without per-step host reads: ep_reward /
+ * ep_len f32[num_envs] running sums, totals f64[6] += {episodes, sum reward, sum length, wins,
+ * losses, draws} of the episodes that finished this step. */
+int mnk_episode_stats(const float* rewards, const uint8_t* dones, int64_t num_envs, float* ep_reward, float* ep_len,
+                      double* totals, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,6 +245,33 @@ def gen_random_policy(seed):
     return {"mask": pack(mask), "cells": np.array(81), "first_legal": act.numpy()}
 
 
+def gen_rollout_buffer(seed):
+    """RolloutBuffer.add / compute_advantages_and_returns (src/alg/rollout_buffer.py:47-80) on random data."""
+    import importlib
+    rb = importlib.import_module("alg.rollout_buffer")
+    rng = np.random.default_rng(seed)
+    steps, ne, m, n = 37, 19, 3, 3
+    buf = rb.RolloutBuffer(steps, ne, (2, m, n), m * n, device="cpu")
+    obs = (rng.random((steps, ne, 2, m, n)) < 0.3).astype(np.float32)
+    obs[:, :, 1] *= 1 - obs[:, :, 0]
+    masks = ~(obs[:, :, 0].astype(bool) | obs[:, :, 1].astype(bool)).reshape(steps, ne, m * n)
+    actions = rng.integers(0, m * n, size=(steps, ne))
+    rewards = rng.choice([-1.0, 0.0, 0.0, 0.0, 1.0], size=(steps, ne)).astype(np.float32)
+    values = rng.normal(size=(steps, ne)).astype(np.float32)
+    logp = -rng.random((steps, ne)).astype(np.float32) * 3
+    dones = rng.random((steps, ne)) < 0.15
+    last = rng.normal(size=ne).astype(np.float32)
+    for t in range(steps):
+        buf.add(*[torch.from_numpy(x[t]) for x in (obs, actions, rewards)], torch.from_numpy(values[t]).view(-1, 1),
+                torch.from_numpy(logp[t]), torch.from_numpy(dones[t]), torch.from_numpy(masks[t]))
+    buf.compute_advantages_and_returns(torch.from_numpy(last), 0.99, 0.95)
+    return {"geom": np.array([steps, ne, m, n]), "obs": pack(obs.reshape(steps * ne, -1)), "masks": pack(masks.reshape(steps * ne, -1)),
+            "actions": actions, "rewards": rewards, "values": values, "log_probs": logp, "dones": dones, "last_values": last,
+            "gamma": np.float32(0.99), "lam": np.float32(0.95), "advantages": buf.advantages.numpy().copy(),
+            "returns": buf.returns.numpy().copy(), "stored_obs": pack(buf.observations.numpy().reshape(steps * ne, -1)),
+            "stored_masks": pack(buf.action_masks.numpy().reshape(steps * ne, -1))}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -262,6 +289,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"wrapper_trace_{m}x{n}x{k}_{tag}.npz"),
                             **gen_wrapper_trace(m, n, k, ne, st, 300 + i, opt))
     np.savez_compressed(os.path.join(OUT, "random_policy_first_legal.npz"), **gen_random_policy(7))
+    np.savez_compressed(os.path.join(OUT, "rollout_buffer_gae.npz"), **gen_rollout_buffer(9))
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} fixtures, {total / 1024:.1f} KiB -> {os.path.normpath(OUT)}")
 

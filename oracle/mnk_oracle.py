@@ -279,3 +279,21 @@ def random_legal_actions(mask: np.ndarray, seed: int, counter: int, env_offset: 
 def side_draw(seed: int, global_env_ids: np.ndarray, episode_counter) -> np.ndarray:
     """Contract of the wrapper's on-device side assignment: lowest Philox bit."""
     return (_draw_u32(seed, global_env_ids, episode_counter, STREAM_SIDE) & np.uint32(1)).astype(np.int64)
+
+
+def gae(rewards, values, dones, last_values, gamma, lam):
+    """RolloutBuffer.compute_advantages_and_returns (src/alg/rollout_buffer.py:60-80) in float32,
+    same operation order as the reference's tensor expressions."""
+    f = np.float32
+    rewards, values = rewards.astype(f), values.astype(f)
+    steps, n = rewards.shape
+    adv = np.zeros((steps, n), dtype=f)
+    last_gae = np.zeros(n, dtype=f)
+    gamma, lam = f(gamma), f(lam)
+    for t in reversed(range(steps)):
+        next_values = last_values.astype(f) if t == steps - 1 else values[t + 1]
+        nnt = f(1.0) - dones[t].astype(f)
+        delta = rewards[t] + gamma * next_values * nnt - values[t]
+        last_gae = delta + gamma * lam * nnt * last_gae
+        adv[t] = last_gae
+    return adv, adv + values

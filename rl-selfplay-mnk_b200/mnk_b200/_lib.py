@@ -102,6 +102,10 @@ SIGNATURES = {
     "mnk_selfplay_agent": (_I32, [_ST, _SP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
     "mnk_selfplay_opponent": (_I32, [_ST, _SP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
     "mnk_selfplay_step_random": (_I32, [_ST, _SP, _VP, _VP, _U64, _VP, _VP, _VP, _VP, _U32, _VP]),
+    "mnk_rollout_store_obs": (_I32, [_ST, _VP, _VP, _VP]),
+    "mnk_rollout_gather": (_I32, [_I32, _I32, _I32, _VP, _I64, _VP, _I64, _VP, _VP, _VP]),
+    "mnk_gae": (_I32, [_VP, _VP, _VP, _VP, _I64, _I64, ctypes.c_float, ctypes.c_float, _VP, _VP, _VP]),
+    "mnk_episode_stats": (_I32, [_VP, _VP, _I64, _VP, _VP, _VP, _VP]),
 }
 
 

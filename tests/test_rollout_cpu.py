@@ -1,0 +1,62 @@
+"""CPU tests of the rollout host logic: the oracle's GAE against the reference's RolloutBuffer
+(golden), shard arithmetic, and the N>1 statistics all-reduce over gloo with world_size 2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import golden_io as gio
+from oracle import mnk_oracle as orc
+from mnk_b200 import dist as mdist
+
+
+def test_oracle_gae_matches_reference_buffer():
+    g = gio.load(gio.files("rollout_buffer_gae")[0])
+    adv, ret = orc.gae(g["rewards"], g["values"], g["dones"], g["last_values"], float(g["gamma"]), float(g["lam"]))
+    assert np.array_equal(adv, g["advantages"]) and np.array_equal(ret, g["returns"])
+    assert np.array_equal(g["stored_obs"], g["obs"]) and np.array_equal(g["stored_masks"], g["masks"])
+
+
+def test_shard_partition():
+    for total, world in [(65536, 8), (1000, 3), (7, 8), (4194304, 8), (5, 1)]:
+        spans = [mdist.shard(total, world, r) for r in range(world)]
+        assert sum(c for c, _ in spans) == total
+        pos = 0
+        for c, off in spans:
+            assert off == pos and c >= 0
+            pos += c
+        assert max(c for c, _ in spans) - min(c for c, _ in spans) <= 1
+    with pytest.raises(ValueError):
+        mdist.shard(10, 2, 2)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    r, w, _ = mdist.init_from_env(backend="gloo")
+    count, offset = mdist.shard(1001, w, r)
+    # each rank accounts for its own shard: {episodes, reward sum, length sum, wins, losses, draws}
+    ids = torch.arange(offset, offset + count, dtype=torch.float64)
+    stats = torch.stack([torch.tensor(float(count), dtype=torch.float64), ids.sum(), (ids * 2).sum(),
+                         (ids % 3 == 0).double().sum(), (ids % 3 == 1).double().sum(), (ids % 3 == 2).double().sum()])
+    mdist.reduce_stats(stats)
+    t_ms = torch.tensor([10.0 + rank], dtype=torch.float64)
+    mdist.reduce_stats(t_ms, op=dist.ReduceOp.MAX)          # bench.py takes the max time over ranks
+    out[rank] = (stats.tolist(), t_ms.item())
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_stats_allreduce():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        ids = np.arange(1001, dtype=np.float64)
+        want = [1001.0, ids.sum(), 2 * ids.sum(), (ids % 3 == 0).sum(), (ids % 3 == 1).sum(), (ids % 3 == 2).sum()]
+        for rank in range(world):
+            stats, tmax = out[rank]
+            assert stats == want and tmax == 11.0
