@@ -272,6 +272,51 @@ def gen_rollout_buffer(seed):
             "stored_masks": pack(buf.action_masks.numpy().reshape(steps * ne, -1))}
 
 
+def gen_resnet(seed, m, n, k, batch):
+    """Eval-mode forward of the reference's default network "resnet_b_s" (configs.py:28-35,
+    resnet.py:73-95) with randomised weights AND BatchNorm statistics, on positions from random play."""
+    import importlib
+    cfg = importlib.import_module("alg.architectures.configs")
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    net = cfg.ResNetSActorCritic((2, m, n), m * n)
+    with torch.no_grad():
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.3)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.7, 1.3)
+                mod.bias.normal_(0, 0.2)
+            elif isinstance(mod, (torch.nn.Conv2d, torch.nn.Linear)):
+                mod.bias.normal_(0, 0.1)
+            elif isinstance(mod, torch.nn.LayerNorm):
+                mod.weight.uniform_(0.8, 1.2)
+                mod.bias.normal_(0, 0.1)
+        net.policy_head[7].weight.mul_(60.0)        # the reference initialises this layer with gain 0.01: scale the
+    net.eval()                                      # logits up so that the parity check is not vacuous
+    env = TorchVectorMnkEnv(m, n, k, batch, device="cpu")
+    obs = env.reset()
+    depth = rng.integers(0, m * n - 1, size=batch)
+    for t in range(m * n - 1):
+        a = RandomPolicy(m * n).act(obs)
+        idx = torch.from_numpy(np.nonzero(depth > t)[0])
+        if len(idx) == 0:
+            break
+        obs, _, _ = env.step_subset(a[idx], idx)
+    x = obs["observation"].clone()
+    flip = torch.from_numpy(rng.random(batch) < 0.5)
+    x[flip] = torch.flip(x[flip], dims=(1,))
+    mask = obs["action_mask"].clone()
+    mask[0] = False                                 # an all-masked row
+    with torch.no_grad():
+        dist, value = net(x, mask)
+        body = net.forward_body(x)
+    out = {f"param/{key}": v.numpy() for key, v in net.state_dict().items()}
+    out.update(geom=np.array([m, n, k, batch]), obs=pack(x.numpy()), mask=pack(mask.numpy()), logits=dist.logits.numpy(),
+               value=value.numpy(), body_absmax=np.float32(body.abs().max().item()))
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -290,6 +335,8 @@ def main():
                             **gen_wrapper_trace(m, n, k, ne, st, 300 + i, opt))
     np.savez_compressed(os.path.join(OUT, "random_policy_first_legal.npz"), **gen_random_policy(7))
     np.savez_compressed(os.path.join(OUT, "rollout_buffer_gae.npz"), **gen_rollout_buffer(9))
+    np.savez_compressed(os.path.join(OUT, "resnet_b_s_9x9.npz"), **gen_resnet(11, 9, 9, 5, 96))
+    np.savez_compressed(os.path.join(OUT, "resnet_b_s_13x13.npz"), **gen_resnet(12, 13, 13, 5, 24))
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} fixtures, {total / 1024:.1f} KiB -> {os.path.normpath(OUT)}")
 

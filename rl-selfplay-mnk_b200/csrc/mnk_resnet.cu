@@ -1,0 +1,318 @@
+// mnk_resnet.cu -- the residual tower of the reference's default policy/value network on tcgen05.
+//
+// Network (reference: src/alg/architectures/resnet.py:8-95 with the "resnet_b_s" parameters of
+// src/alg/architectures/configs.py:28-35): conv3x3(2->32)+BN+ReLU, then `blocks` x
+// [conv3x3+BN+ReLU, conv3x3+BN, +skip, ReLU], then the 1x1 convolutions that open the policy head
+// (32->2) and the value head (32->1).  Eval-mode BatchNorm is folded into the convolution weights
+// and biases on the host.  These convolutions are 98% of the forward's FLOPs and the
+// only dense contraction on the hot path; the heads' LayerNorm/Linear layers that follow operate on
+// the [N, 2*cells] / [N, cells] features this kernel writes.
+//
+// Formulation: implicit GEMM, D[pixel][c_out] = sum_{tap, c_in} A[pixel + off(tap)][c_in] * W[tap][c_out][c_in].
+//   * A CTA owns SPC consecutive envs.  Each env's m x n board is laid out on pixel rows with row
+//     stride PW = n+1 (the same guard-column trick as the bitboards) and PW+1 zero rows between
+//     envs, so a 3x3 tap is a constant row offset off = dr*PW + dc and out-of-board neighbours read
+//     zeros.  The tile is 1024 pixel rows = 8 UMMA M-blocks of 128.
+//   * Activations live in shared memory as bf16 in the canonical K-major NO-SWIZZLE UMMA layout
+//     [k-chunk (8 channels = 16 B)][row][16 B] with SBO = 128 B, i.e. consecutive rows are 16 B
+//     apart: shifting the operand by `off` rows is just a different start address in the shared
+//     memory descriptor.  No im2col, no data movement between layers: the whole tower runs out of
+//     two ping-pong activation buffers (A0 scratch, A1 running feature map).
+//   * One thread issues tcgen05.mma (M=128, N=32, K=16, bf16 -> fp32): 18 per M-block per layer,
+//     accumulating in TMEM (8 blocks x 32 columns = 256 columns), and commits each block to an
+//     mbarrier.  Four epilogue warps (one per TMEM lane quarter) wait per block, tcgen05.ld the 32
+//     fp32 channels of their pixel row, add bias (+ skip), ReLU, write bf16 back to shared memory --
+//     so the epilogue of block j overlaps the MMAs of blocks j+1...  Guard rows are rewritten as zeros.
+//   * Layer weights (18 KB) stream through a 2-deep shared-memory ring with 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx) issued one layer ahead.
+//   * The input is read straight from the packed bitboards (72 B per env at 9x9) and the last
+//     epilogue applies the two 1x1 head convolutions from fp32 registers and stores the features.
+#include "mnk_dispatch.cuh"
+
+#include <cuda_bf16.h>
+
+namespace rn {
+constexpr int kC = 32;                        // tower channels
+constexpr int kBlocksM = 8;                   // UMMA M-blocks per CTA
+constexpr int kRows = 128 * kBlocksM;         // pixel rows per CTA tile
+constexpr int kMargin = 40;                   // zero rows before/after the tile (>= n+2 for n <= 32, multiple of 8)
+constexpr int kBufRows = kRows + 2 * kMargin; // rows per activation buffer
+constexpr int kChunks = kC / 8;               // 16-byte k-chunks per row
+constexpr int kActBytes = kChunks * kBufRows * 16;
+constexpr int kTaps = 9;
+constexpr int kLayerWeightBytes = kTaps * kChunks * kC * 16;   // [tap][k-chunk][c_out][8 c_in] bf16
+constexpr int kThreads = 160;                 // warps 0-3 epilogue, warp 4 MMA issue + TMA
+constexpr int kTmemCols = 32 * kBlocksM;      // 256
+constexpr int kMaxLayers = 1 + 2 * 8;
+
+struct Smem {
+    alignas(128) unsigned char act[2][kActBytes];
+    alignas(128) unsigned char wts[2][kLayerWeightBytes];
+    alignas(16) float bias[kMaxLayers][kC];
+    alignas(16) float head_w[3][kC];
+    float head_b[4];
+    alignas(8) unsigned long long mma_bar[kBlocksM];
+    alignas(8) unsigned long long wts_bar[2];
+    unsigned int tmem_base;
+};
+
+MNK_DEV u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+MNK_DEV void mbar_init(void* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+MNK_DEV void mbar_expect_tx(void* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: returns false instead of hanging if the phase never completes
+MNK_DEV bool mbar_wait(void* bar, u32 parity) {
+    const u32 addr = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 20); ++spin) {
+        u32 done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+MNK_DEV void tma_bulk_g2s(void* dst, const void* src, u32 bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor: start address, LBO (distance between the two
+// 16-byte k-chunks of one MMA), SBO (distance between 8-row groups), version = 1 (Blackwell)
+MNK_DEV u64 umma_desc(u32 saddr, u32 lbo_bytes, u32 sbo_bytes) {
+    return (u64)((saddr & 0x3FFFFu) >> 4) | ((u64)(lbo_bytes >> 4) << 16) | ((u64)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = 32
+constexpr u32 kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(kC >> 3) << 17) | ((128u >> 4) << 24);
+
+MNK_DEV void umma_bf16(u32 tmem_d, u64 desc_a, u64 desc_b, u32 accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+MNK_DEV void umma_commit(void* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+MNK_DEV void tmem_ld32(u32 taddr, u32 (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Params {
+    int m, n, words, layers;          // layers = 1 + 2*blocks
+    long long num_envs;
+    int spc;                          // envs per CTA
+    int pw, rs;                       // pixel-row stride n+1, env stride m*pw + pw + 1
+    const u64* bits;                  // u64[2][words][num_envs]
+    const u8* swap;                   // u8[num_envs] or NULL: 1 => the mover/agent is white, planes exchanged
+    const unsigned char* weights;     // bf16 [layers][tap][k-chunk][c_out][8]
+    const float* bias;                // f32 [layers][32]   (BN folded)
+    const float* head_w;              // f32 [3][32]: policy ch0, policy ch1, value 1x1 conv
+    const float* head_b;              // f32 [3]
+    float* policy_feat;               // f32 [num_envs][2*cells]
+    float* value_feat;                // f32 [num_envs][cells]
+    int* error;                       // set to 1 on an mbarrier timeout
+};
+
+__global__ void __launch_bounds__(kThreads, 1) resnet_tower_kernel(Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long env0 = (long long)blockIdx.x * p.spc;
+    const int cells = p.m * p.n;
+    const int envs_here = (int)min((long long)p.spc, p.num_envs - env0);
+
+    // ---- one-time setup -----------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int j = 0; j < kBlocksM; ++j) mbar_init(&sm.mma_bar[j], 1);
+        mbar_init(&sm.wts_bar[0], 1);
+        mbar_init(&sm.wts_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {   // TMEM allocation is a warp-wide operation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    {   // zero both activation buffers, load biases / head weights
+        uint4* z = reinterpret_cast<uint4*>(&sm.act[0][0]);
+        for (int i = tid; i < 2 * kActBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = tid; i < p.layers * kC; i += kThreads) (&sm.bias[0][0])[i] = p.bias[i];
+        for (int i = tid; i < 3 * kC; i += kThreads) (&sm.head_w[0][0])[i] = p.head_w[i];
+        if (tid < 3) sm.head_b[tid] = p.head_b[tid];
+    }
+    __syncthreads();
+    // input: the two canonical planes of each env into channels 0,1 of buffer A0 (k-chunk 0)
+    for (int idx = tid; idx < envs_here * cells; idx += kThreads) {
+        const int s = idx / cells, cell = idx - s * cells;
+        const int r = cell / p.n, bit = cell + r;   // bit index in the guard-strided bitboard == row offset in the tile
+        const long long e = env0 + s;
+        const u64 wb = p.bits[(size_t)(bit >> 6) * p.num_envs + e];
+        const u64 ww = p.bits[(size_t)(p.words + (bit >> 6)) * p.num_envs + e];
+        const bool sw = p.swap != nullptr && p.swap[e] != 0;
+        const u32 black = (u32)(wb >> (bit & 63)) & 1u, white = (u32)(ww >> (bit & 63)) & 1u;
+        const u32 me = sw ? white : black, enemy = sw ? black : white;
+        const int row = kMargin + s * p.rs + bit;
+        reinterpret_cast<uint4*>(&sm.act[0][0])[row] = make_uint4(me * 0x3F80u | (enemy * 0x3F80u) << 16, 0, 0, 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const u32 tmem_base = sm.tmem_base;
+    bool ok = true;
+
+    if (warp == 4 && lane == 0) {   // first layer's weights
+        mbar_expect_tx(&sm.wts_bar[0], kLayerWeightBytes);
+        tma_bulk_g2s(&sm.wts[0][0], p.weights, kLayerWeightBytes, &sm.wts_bar[0]);
+    }
+
+    for (int L = 0; L < p.layers; ++L) {
+        const int in_buf = (L & 1) ? 1 : 0, out_buf = in_buf ^ 1;
+        const bool skip = (L >= 2) && ((L & 1) == 0);        // second conv of a residual block adds A1
+        const bool last = (L == p.layers - 1);
+        if (warp == 4) {
+            if (lane == 0) {
+                if (L + 1 < p.layers) {   // prefetch next layer's weights into the other ring slot
+                    mbar_expect_tx(&sm.wts_bar[(L + 1) & 1], kLayerWeightBytes);
+                    tma_bulk_g2s(&sm.wts[(L + 1) & 1][0], p.weights + (size_t)(L + 1) * kLayerWeightBytes, kLayerWeightBytes,
+                                 &sm.wts_bar[(L + 1) & 1]);
+                }
+                ok = ok && mbar_wait(&sm.wts_bar[L & 1], (L >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const u32 a_base = smem_u32(&sm.act[in_buf][0]);
+                const u32 w_base = smem_u32(&sm.wts[L & 1][0]);
+                const int ksteps = (L == 0) ? 1 : kC / 16;   // the input layer has 2 real channels: one K=16 step
+                for (int j = 0; j < kBlocksM; ++j) {
+                    u32 acc = 0;
+                    for (int tap = 0; tap < kTaps; ++tap) {
+                        const int off = (tap / 3 - 1) * p.pw + (tap % 3 - 1);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const u32 a_addr = a_base + (u32)(2 * ks) * (kBufRows * 16) + (u32)(kMargin + 128 * j + off) * 16;
+                            const u32 b_addr = w_base + (u32)((tap * kChunks + 2 * ks) * kC) * 16;
+                            umma_bf16(tmem_base + 32 * j, umma_desc(a_addr, kBufRows * 16, 128), umma_desc(b_addr, kC * 16, 128), acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(&sm.mma_bar[j]);
+                }
+            }
+        } else {
+            const float* bias = sm.bias[L];
+            for (int j = 0; j < kBlocksM; ++j) {
+                ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[j], L & 1)) != 0;   // warp-uniform
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                u32 acc[32];
+                tmem_ld32(tmem_base + ((u32)(warp * 32) << 16) + 32 * j, acc);
+                const int i = 128 * j + warp * 32 + lane;        // pixel row of this thread
+                const int s = i / p.rs, q = i - s * p.rs;
+                const int r = q / p.pw, c = q - r * p.pw;
+                const bool valid = s < envs_here && r < p.m && c < p.n;
+                float v[32];
+                uint4* out_row[kChunks];
+#pragma unroll
+                for (int kc = 0; kc < kChunks; ++kc)
+                    out_row[kc] = reinterpret_cast<uint4*>(&sm.act[out_buf][0]) + (size_t)kc * kBufRows + (kMargin + i);
+#pragma unroll
+                for (int ch = 0; ch < 32; ++ch) v[ch] = __uint_as_float(acc[ch]) + bias[ch];
+                if (skip) {
+#pragma unroll
+                    for (int kc = 0; kc < kChunks; ++kc) {
+                        const uint4 rsd = *out_row[kc];
+                        const u32 w[4] = {rsd.x, rsd.y, rsd.z, rsd.w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            v[kc * 8 + 2 * h] += __uint_as_float(w[h] << 16);
+                            v[kc * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xFFFF0000u);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int ch = 0; ch < 32; ++ch) v[ch] = valid ? fmaxf(v[ch], 0.0f) : 0.0f;
+                if (!last) {
+#pragma unroll
+                    for (int kc = 0; kc < kChunks; ++kc) {
+                        u32 w[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const __nv_bfloat162 pr = __floats2bfloat162_rn(v[kc * 8 + 2 * h], v[kc * 8 + 2 * h + 1]);
+                            w[h] = *reinterpret_cast<const u32*>(&pr);
+                        }
+                        *out_row[kc] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                } else if (valid) {   // the 1x1 convolutions that open the two heads, from fp32 registers
+                    float h0 = sm.head_b[0], h1 = sm.head_b[1], h2 = sm.head_b[2];
+#pragma unroll
+                    for (int ch = 0; ch < 32; ++ch) {
+                        h0 = fmaf(v[ch], sm.head_w[0][ch], h0);
+                        h1 = fmaf(v[ch], sm.head_w[1][ch], h1);
+                        h2 = fmaf(v[ch], sm.head_w[2][ch], h2);
+                    }
+                    const long long e = env0 + s;
+                    const int cell = r * p.n + c;
+                    p.policy_feat[(size_t)e * 2 * cells + cell] = h0;
+                    p.policy_feat[(size_t)e * 2 * cells + cells + cell] = h1;
+                    p.value_feat[(size_t)e * cells + cell] = h2;
+                }
+            }
+        }
+        // layer boundary: epilogue stores -> visible to the async proxy (UMMA reads), TMEM reads done
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (!ok && p.error != nullptr) atomicExch(p.error, 1);
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+}  // namespace rn
+
+extern "C" int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, const void* weights, const float* bias,
+                                const float* head_w, const float* head_b, int32_t blocks, float* policy_feat,
+                                float* value_feat, int32_t* error, void* stream) {
+    if (int rc = mnk_check_state(st)) return rc;
+    if (!weights || !bias || !head_w || !head_b || !policy_feat || !value_feat) return MNK_ERR_NULL;
+    if (blocks < 1 || blocks > 8) return MNK_ERR_ARG;
+    if (reinterpret_cast<uintptr_t>(weights) & 15u) return MNK_ERR_ALIGN;
+    if (st->num_envs == 0) return MNK_OK;
+    rn::Params p;
+    p.m = st->m; p.n = st->n; p.words = st->words; p.layers = 1 + 2 * blocks;
+    p.num_envs = st->num_envs;
+    p.pw = st->n + 1;
+    p.rs = st->m * p.pw + p.pw + 1;
+    p.spc = rn::kRows / p.rs;
+    if (p.spc < 1 || p.pw + 1 > rn::kMargin) return MNK_ERR_GEOM;
+    p.bits = reinterpret_cast<const u64*>(st->bits);
+    p.swap = swap; p.weights = static_cast<const unsigned char*>(weights); p.bias = bias;
+    p.head_w = head_w; p.head_b = head_b; p.policy_feat = policy_feat; p.value_feat = value_feat; p.error = error;
+    const size_t smem = sizeof(rn::Smem) + 128;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(rn::resnet_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const unsigned grid = (unsigned)((st->num_envs + p.spc - 1) / p.spc);
+    rn::resnet_tower_kernel<<<grid, rn::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    return mnk_launch_status();
+}

@@ -11,7 +11,10 @@ from .policy import NNPolicy, Policy, RandomPolicy  # noqa: F401
 from .sampling import MaskedCategorical, masked_sample  # noqa: F401
 from .wrapper import TorchSelfPlayWrapper  # noqa: F401
 from .rollout import RolloutBuffer, RolloutCollector, RolloutStats  # noqa: F401
+from .nets import ResNetActorCritic  # noqa: F401
+from .resnet import NativeNNPolicy, NativeResNet  # noqa: F401
 from . import dist  # noqa: F401
 
 __all__ = ["build", "lib", "LIB_PATH", "TorchVectorMnkEnv", "TorchSelfPlayWrapper", "Policy", "RandomPolicy", "NNPolicy",
-           "MaskedCategorical", "masked_sample", "RolloutBuffer", "RolloutCollector", "RolloutStats", "dist"]
+           "MaskedCategorical", "masked_sample", "RolloutBuffer", "RolloutCollector", "RolloutStats", "dist",
+           "ResNetActorCritic", "NativeResNet", "NativeNNPolicy"]

@@ -106,6 +106,7 @@ SIGNATURES = {
     "mnk_rollout_gather": (_I32, [_I32, _I32, _I32, _VP, _I64, _VP, _I64, _VP, _VP, _VP]),
     "mnk_gae": (_I32, [_VP, _VP, _VP, _VP, _I64, _I64, ctypes.c_float, ctypes.c_float, _VP, _VP, _VP]),
     "mnk_episode_stats": (_I32, [_VP, _VP, _I64, _VP, _VP, _VP, _VP]),
+    "mnk_resnet_tower": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
 }
 
 

@@ -1,0 +1,135 @@
+"""tcgen05 forward of the reference's default network, fed from bitboards.
+
+``NativeResNet`` takes a torch module with the reference's ResNet layout (``conv_in``,
+``res_blocks[i].conv1/bn1/conv2/bn2``, ``policy_head``, ``value_head``; src/alg/architectures/
+resnet.py:24-65) with 32 channels, folds eval-mode BatchNorm into the convolutions, lays the bf16
+weights out for the UMMA B operand and runs the whole convolutional part -- 98% of the forward's
+FLOPs -- as ONE kernel (``mnk_resnet_tower``, csrc/mnk_resnet.cu) straight from the packed env
+state.  The heads' LayerNorm / Linear stack (plain small GEMMs, 2% of the FLOPs) runs through the
+original torch modules on the features the kernel writes.  Inference only (NNPolicy / opponent /
+rollout forward); the learner keeps the torch module.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import MnkState, check
+from .policy import Policy
+from .sampling import MaskedCategorical, masked_sample
+
+
+def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tensor]:
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    w = conv.weight * scale[:, None, None, None]
+    b = (conv.bias - bn.running_mean) * scale + bn.bias
+    return w.float(), b.float()
+
+
+def _arrange(w: torch.Tensor) -> torch.Tensor:
+    """[c_out=32][c_in<=32][3][3] fp32 -> bf16 [tap][k-chunk=4][c_out][8 c_in] (zero-padded input channels)."""
+    c_out, c_in = w.shape[0], w.shape[1]
+    full = torch.zeros((c_out, 32, 3, 3), dtype=torch.float32, device=w.device)
+    full[:, :c_in] = w
+    t = full.permute(2, 3, 1, 0).reshape(9, 4, 8, c_out)          # [tap][kc][j][c_out]
+    return t.permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)   # [tap][kc][c_out][j]
+
+
+class NativeResNet:
+    def __init__(self, model: nn.Module, device="cuda"):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("mnk_b200.NativeResNet: CUDA only (no CPU fallback)")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self._dev = dev
+        self._L = _lib.lib()
+        self.refresh(model)
+
+    @torch.no_grad()
+    def refresh(self, model: nn.Module):
+        """(Re)import weights -- call after the learner updated `model`."""
+        convs = [(model.conv_in[0], model.conv_in[1])]
+        for blk in model.res_blocks:
+            convs += [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2)]
+        if any(c.out_channels != 32 or tuple(c.kernel_size) != (3, 3) for c, _ in convs):
+            raise ValueError("NativeResNet supports the 32-channel 3x3 tower (resnet_b_s)")
+        self.blocks = len(model.res_blocks)
+        folded = [_fold(c, b) for c, b in convs]
+        dev = self._dev
+        self.weights = torch.stack([_arrange(w.to(dev)) for w, _ in folded]).contiguous()    # bf16 [L][9][4][32][8]
+        self.bias = torch.stack([b.to(dev) for _, b in folded]).contiguous()                  # f32 [L][32]
+        pc, vc = model.policy_head[0], model.value_head[0]
+        self.head_w = torch.cat([pc.weight.reshape(2, 32), vc.weight.reshape(1, 32)]).float().to(dev).contiguous()
+        self.head_b = torch.cat([pc.bias.reshape(2), vc.bias.reshape(1)]).float().to(dev).contiguous()
+        self.policy_tail = nn.Sequential(*list(model.policy_head)[2:]).to(dev).eval()        # LN, ReLU, Linear, LN, ReLU, Linear
+        self.value_tail = nn.Sequential(*list(model.value_head)[2:]).to(dev).eval()          # ... + Tanh
+        self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    @torch.no_grad()
+    def features(self, state: MnkState, num_envs: int, cells: int, swap: Optional[torch.Tensor]):
+        pf = torch.empty((num_envs, 2 * cells), dtype=torch.float32, device=self._dev)
+        vf = torch.empty((num_envs, cells), dtype=torch.float32, device=self._dev)
+        with torch.cuda.device(self._dev):
+            check(self._L.mnk_resnet_tower(ctypes.byref(state), None if swap is None else swap.data_ptr(),
+                                            self.weights.data_ptr(), self.bias.data_ptr(), self.head_w.data_ptr(),
+                                            self.head_b.data_ptr(), self.blocks, pf.data_ptr(), vf.data_ptr(),
+                                            self._err.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream),
+                  "mnk_resnet_tower")
+        return pf, vf
+
+    @torch.no_grad()
+    def forward_env(self, env, swap: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Raw policy logits f32[N, m*n] and value f32[N, 1] for the CURRENT state of `env`, read from its
+        bitboards; `swap` u8[N] != 0 exchanges the planes (the canonical view of a white mover/agent)."""
+        env._fold_mirrors()
+        pf, vf = self.features(env._st, env.num_envs, env.m * env.n, swap)
+        return self.policy_tail(pf), self.value_tail(vf)
+
+    @torch.no_grad()
+    def forward(self, obs: torch.Tensor, action_mask: Optional[torch.Tensor] = None):
+        """Module-compatible forward(obs f32[B,2,m,n], mask) -> (MaskedCategorical, value[B,1]): the
+        observation is packed to bitboards first (mnk_pack_boards), then the same kernel runs."""
+        if obs.dim() == 3:
+            obs = obs.unsqueeze(0)
+        b, _, m, n = obs.shape
+        words = self._L.mnk_state_words(m, n)
+        bits = torch.empty((2, words, b), dtype=torch.int64, device=self._dev)
+        meta = torch.zeros(b, dtype=torch.int32, device=self._dev)
+        st = MnkState(m, n, 1, words, b, bits.data_ptr(), meta.data_ptr())
+        obs = obs.to(self._dev, torch.float32).contiguous()
+        with torch.cuda.device(self._dev):
+            check(self._L.mnk_pack_boards(ctypes.byref(st), obs.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream),
+                  "mnk_pack_boards")
+        pf, vf = self.features(st, b, m * n, None)
+        logits, value = self.policy_tail(pf), self.value_tail(vf)
+        if action_mask is not None and action_mask.dim() == 1:
+            action_mask = action_mask.unsqueeze(0)
+        return MaskedCategorical(logits, action_mask), value
+
+    __call__ = forward
+
+    def check_error(self):
+        """Raises if any launch hit an internal barrier timeout (one device->host read)."""
+        if int(self._err.item()) != 0:
+            raise RuntimeError("mnk_resnet_tower: internal barrier wait timed out")
+
+
+class NativeNNPolicy(Policy):
+    """NNPolicy (src/selfplay/policy.py:32-54) on the tcgen05 forward."""
+
+    def __init__(self, model: nn.Module, device="cuda", seed: int = 0):
+        model.eval()
+        self.net = NativeResNet(model, device=device)
+        self.seed = seed
+        self._calls = 0
+
+    def act(self, obs, deterministic: bool = False) -> torch.Tensor:
+        dist, _ = self.net.forward(obs["observation"], obs["action_mask"])
+        self._calls += 1
+        return masked_sample(dist._raw, dist._mask, seed=self.seed, counter=self._calls, deterministic=deterministic,
+                             want_log_prob=False)[0]
