@@ -41,7 +41,10 @@ constexpr int kChunks = kC / 8;               // 16-byte k-chunks per row
 constexpr int kActBytes = kChunks * kBufRows * 16;
 constexpr int kTaps = 9;
 constexpr int kLayerWeightBytes = kTaps * kChunks * kC * 16;   // [tap][k-chunk][c_out][8 c_in] bf16
-constexpr int kThreads = 160;                 // warps 0-3 epilogue, warp 4 MMA issue + TMA
+constexpr int kGroupBlocks = 4;               // M-blocks whose MMAs are interleaved (independent accumulators)
+constexpr int kGroups = kBlocksM / kGroupBlocks;
+constexpr int kMmaWarp = 8;                   // warps 0-7 epilogue (lane quarter = warp&3, channel half = warp>>2)
+constexpr int kThreads = 32 * (kMmaWarp + 1); // warp 8: MMA issue + TMA
 constexpr int kTmemCols = 32 * kBlocksM;      // 256
 constexpr int kMaxLayers = 1 + 2 * 8;
 
@@ -57,6 +60,12 @@ struct Smem {
 };
 
 MNK_DEV u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+MNK_DEV bool elect_one() {   // one lane of a converged warp
+    u32 pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 MNK_DEV void mbar_init(void* bar, u32 count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -133,6 +142,55 @@ struct Params {
     int* error;                       // set to 1 on an mbarrier timeout
 };
 
+MNK_DEV void tmem_ld16(u32 taddr, u32 (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// bias (+ skip) + ReLU + bf16 store of NCH channels [ch0, ch0+NCH) of pixel row i; returns the fp32 values
+template <int NCH>
+MNK_DEV void epilogue_row(Smem& sm, const u32* acc, const float* bias, int out_buf, int i, int ch0, bool skip, bool valid,
+                          bool store, float (&v)[NCH]) {
+    constexpr int NKC = NCH / 8;
+    uint4* out_row[NKC];
+#pragma unroll
+    for (int kc = 0; kc < NKC; ++kc)
+        out_row[kc] = reinterpret_cast<uint4*>(&sm.act[out_buf][0]) + (size_t)(ch0 / 8 + kc) * kBufRows + (kMargin + i);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) v[ch] = __uint_as_float(acc[ch]) + bias[ch0 + ch];
+    if (skip) {
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+            const uint4 rsd = *out_row[kc];
+            const u32 w[4] = {rsd.x, rsd.y, rsd.z, rsd.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                v[kc * 8 + 2 * h] += __uint_as_float(w[h] << 16);
+                v[kc * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xFFFF0000u);
+            }
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) v[ch] = valid ? fmaxf(v[ch], 0.0f) : 0.0f;
+    if (store) {
+#pragma unroll
+        for (int kc = 0; kc < NKC; ++kc) {
+            u32 w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const __nv_bfloat162 pr = __floats2bfloat162_rn(v[kc * 8 + 2 * h], v[kc * 8 + 2 * h + 1]);
+                w[h] = *reinterpret_cast<const u32*>(&pr);
+            }
+            *out_row[kc] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) resnet_tower_kernel(Params p) {
     extern __shared__ unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -143,12 +201,12 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_kernel(Params p) {
 
     // ---- one-time setup -----------------------------------------------------------------------------
     if (tid == 0) {
-        for (int j = 0; j < kBlocksM; ++j) mbar_init(&sm.mma_bar[j], 1);
+        for (int g = 0; g < kGroups; ++g) mbar_init(&sm.mma_bar[g], 1);
         mbar_init(&sm.wts_bar[0], 1);
         mbar_init(&sm.wts_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {   // TMEM allocation is a warp-wide operation
+    if (warp == kMmaWarp) {   // TMEM allocation is a warp-wide operation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -173,6 +231,17 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_kernel(Params p) {
         const int row = kMargin + s * p.rs + bit;
         reinterpret_cast<uint4*>(&sm.act[0][0])[row] = make_uint4(me * 0x3F80u | (enemy * 0x3F80u) << 16, 0, 0, 0);
     }
+    // which of this thread's 8 pixel rows (one per M-block) are real board cells: fixed for all layers
+    const int quarter = warp & 3, half = (warp >> 2) & 1;
+    u32 valid_bits = 0;
+    if (warp < kMmaWarp) {
+        for (int j = 0; j < kBlocksM; ++j) {
+            const int i = 128 * j + quarter * 32 + lane;
+            const int s = i / p.rs, q = i - s * p.rs;
+            const int r = q / p.pw, c = q - r * p.pw;
+            if (s < envs_here && r < p.m && c < p.n) valid_bits |= 1u << j;
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -180,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_kernel(Params p) {
     const u32 tmem_base = sm.tmem_base;
     bool ok = true;
 
-    if (warp == 4 && lane == 0) {   // first layer's weights
+    if (warp == kMmaWarp && elect_one()) {   // first layer's weights
         mbar_expect_tx(&sm.wts_bar[0], kLayerWeightBytes);
         tma_bulk_g2s(&sm.wts[0][0], p.weights, kLayerWeightBytes, &sm.wts_bar[0]);
     }
@@ -189,88 +258,78 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_kernel(Params p) {
         const int in_buf = (L & 1) ? 1 : 0, out_buf = in_buf ^ 1;
         const bool skip = (L >= 2) && ((L & 1) == 0);        // second conv of a residual block adds A1
         const bool last = (L == p.layers - 1);
-        if (warp == 4) {
-            if (lane == 0) {
-                if (L + 1 < p.layers) {   // prefetch next layer's weights into the other ring slot
-                    mbar_expect_tx(&sm.wts_bar[(L + 1) & 1], kLayerWeightBytes);
-                    tma_bulk_g2s(&sm.wts[(L + 1) & 1][0], p.weights + (size_t)(L + 1) * kLayerWeightBytes, kLayerWeightBytes,
-                                 &sm.wts_bar[(L + 1) & 1]);
-                }
-                ok = ok && mbar_wait(&sm.wts_bar[L & 1], (L >> 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const u32 a_base = smem_u32(&sm.act[in_buf][0]);
-                const u32 w_base = smem_u32(&sm.wts[L & 1][0]);
-                const int ksteps = (L == 0) ? 1 : kC / 16;   // the input layer has 2 real channels: one K=16 step
-                for (int j = 0; j < kBlocksM; ++j) {
-                    u32 acc = 0;
-                    for (int tap = 0; tap < kTaps; ++tap) {
-                        const int off = (tap / 3 - 1) * p.pw + (tap % 3 - 1);
-                        for (int ks = 0; ks < ksteps; ++ks) {
-                            const u32 a_addr = a_base + (u32)(2 * ks) * (kBufRows * 16) + (u32)(kMargin + 128 * j + off) * 16;
-                            const u32 b_addr = w_base + (u32)((tap * kChunks + 2 * ks) * kC) * 16;
-                            umma_bf16(tmem_base + 32 * j, umma_desc(a_addr, kBufRows * 16, 128), umma_desc(b_addr, kC * 16, 128), acc);
-                            acc = 1;
+        if (warp == kMmaWarp) {
+            // The whole warp runs this (warp-uniform) control flow and ONE elected lane issues each
+            // tcgen05 / TMA instruction: with a divergent `if (lane == 0)` region the compiler cannot
+            // prove the descriptors uniform and wraps every MMA in an ELECT/R2UR waterfall loop
+            // (~100 cycles per MMA on the issuing thread; ncu source page, profiles/).
+            if (L + 1 < p.layers && elect_one()) {   // prefetch next layer's weights into the other ring slot
+                mbar_expect_tx(&sm.wts_bar[(L + 1) & 1], kLayerWeightBytes);
+                tma_bulk_g2s(&sm.wts[(L + 1) & 1][0], p.weights + (size_t)(L + 1) * kLayerWeightBytes, kLayerWeightBytes,
+                             &sm.wts_bar[(L + 1) & 1]);
+            }
+            ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.wts_bar[L & 1], (L >> 1) & 1)) != 0;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const u32 a_base = smem_u32(&sm.act[in_buf][0]);
+            const u32 w_base = smem_u32(&sm.wts[L & 1][0]);
+            const int ksteps = (L == 0) ? 1 : kC / 16;   // the input layer has 2 real channels: one K=16 step
+            // Back-to-back MMAs into ONE accumulator serialise on the accumulate latency; interleaving
+            // the kGroupBlocks M-blocks of a group gives independent chains.
+            for (int g = 0; g < kGroups; ++g) {
+                u32 acc = 0;
+                for (int tap = 0; tap < kTaps; ++tap) {
+                    const int off = (tap / 3 - 1) * p.pw + (tap % 3 - 1);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const u64 b_desc = umma_desc(w_base + (u32)((tap * kChunks + 2 * ks) * kC) * 16, kC * 16, 128);
+                        const u32 a_addr0 = a_base + (u32)(2 * ks) * (kBufRows * 16) + (u32)(kMargin + 128 * g * kGroupBlocks + off) * 16;
+                        const u64 a_desc0 = umma_desc(a_addr0, kBufRows * 16, 128);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int jj = 0; jj < kGroupBlocks; ++jj)   // next M-block: +128 rows = +2048 B = +128 in the address field
+                                umma_bf16(tmem_base + 32 * (g * kGroupBlocks + jj), a_desc0 + (u64)(128 * jj), b_desc, acc);
                         }
+                        __syncwarp();
+                        acc = 1;
                     }
-                    umma_commit(&sm.mma_bar[j]);
                 }
+                if (elect_one()) umma_commit(&sm.mma_bar[g]);
+                __syncwarp();
             }
         } else {
             const float* bias = sm.bias[L];
             for (int j = 0; j < kBlocksM; ++j) {
-                ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[j], L & 1)) != 0;   // warp-uniform
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                u32 acc[32];
-                tmem_ld32(tmem_base + ((u32)(warp * 32) << 16) + 32 * j, acc);
-                const int i = 128 * j + warp * 32 + lane;        // pixel row of this thread
-                const int s = i / p.rs, q = i - s * p.rs;
-                const int r = q / p.pw, c = q - r * p.pw;
-                const bool valid = s < envs_here && r < p.m && c < p.n;
-                float v[32];
-                uint4* out_row[kChunks];
-#pragma unroll
-                for (int kc = 0; kc < kChunks; ++kc)
-                    out_row[kc] = reinterpret_cast<uint4*>(&sm.act[out_buf][0]) + (size_t)kc * kBufRows + (kMargin + i);
-#pragma unroll
-                for (int ch = 0; ch < 32; ++ch) v[ch] = __uint_as_float(acc[ch]) + bias[ch];
-                if (skip) {
-#pragma unroll
-                    for (int kc = 0; kc < kChunks; ++kc) {
-                        const uint4 rsd = *out_row[kc];
-                        const u32 w[4] = {rsd.x, rsd.y, rsd.z, rsd.w};
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            v[kc * 8 + 2 * h] += __uint_as_float(w[h] << 16);
-                            v[kc * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xFFFF0000u);
-                        }
-                    }
+                if (j % kGroupBlocks == 0) {
+                    ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[j / kGroupBlocks], L & 1)) != 0;   // warp-uniform
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
+                const int i = 128 * j + quarter * 32 + lane;        // pixel row of this thread
+                const bool valid = (valid_bits >> j) & 1u;
+                if (!last) {   // 8 warps: each takes 16 of the 32 channels of its TMEM lane quarter
+                    u32 acc[16];
+                    float v[16];
+                    tmem_ld16(tmem_base + ((u32)(quarter * 32) << 16) + 32 * j + 16 * half, acc);
+                    epilogue_row<16>(sm, acc, bias, out_buf, i, 16 * half, skip, valid, true, v);
+                } else if (half == 0) {   // last layer: full rows, then the 1x1 convolutions that open the two heads
+                    u32 acc[32];
+                    float v[32];
+                    tmem_ld32(tmem_base + ((u32)(quarter * 32) << 16) + 32 * j, acc);
+                    epilogue_row<32>(sm, acc, bias, out_buf, i, 0, skip, valid, false, v);
+                    if (valid) {
+                        float h0 = sm.head_b[0], h1 = sm.head_b[1], h2 = sm.head_b[2];
 #pragma unroll
-                for (int ch = 0; ch < 32; ++ch) v[ch] = valid ? fmaxf(v[ch], 0.0f) : 0.0f;
-                if (!last) {
-#pragma unroll
-                    for (int kc = 0; kc < kChunks; ++kc) {
-                        u32 w[4];
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const __nv_bfloat162 pr = __floats2bfloat162_rn(v[kc * 8 + 2 * h], v[kc * 8 + 2 * h + 1]);
-                            w[h] = *reinterpret_cast<const u32*>(&pr);
+                        for (int ch = 0; ch < 32; ++ch) {
+                            h0 = fmaf(v[ch], sm.head_w[0][ch], h0);
+                            h1 = fmaf(v[ch], sm.head_w[1][ch], h1);
+                            h2 = fmaf(v[ch], sm.head_w[2][ch], h2);
                         }
-                        *out_row[kc] = make_uint4(w[0], w[1], w[2], w[3]);
+                        const int s = i / p.rs, q = i - s * p.rs;
+                        const int r = q / p.pw, c = q - r * p.pw;
+                        const long long e = env0 + s;
+                        const int cell = r * p.n + c;
+                        p.policy_feat[(size_t)e * 2 * cells + cell] = h0;
+                        p.policy_feat[(size_t)e * 2 * cells + cells + cell] = h1;
+                        p.value_feat[(size_t)e * cells + cell] = h2;
                     }
-                } else if (valid) {   // the 1x1 convolutions that open the two heads, from fp32 registers
-                    float h0 = sm.head_b[0], h1 = sm.head_b[1], h2 = sm.head_b[2];
-#pragma unroll
-                    for (int ch = 0; ch < 32; ++ch) {
-                        h0 = fmaf(v[ch], sm.head_w[0][ch], h0);
-                        h1 = fmaf(v[ch], sm.head_w[1][ch], h1);
-                        h2 = fmaf(v[ch], sm.head_w[2][ch], h2);
-                    }
-                    const long long e = env0 + s;
-                    const int cell = r * p.n + c;
-                    p.policy_feat[(size_t)e * 2 * cells + cell] = h0;
-                    p.policy_feat[(size_t)e * 2 * cells + cells + cell] = h1;
-                    p.value_feat[(size_t)e * cells + cell] = h2;
                 }
             }
         }
@@ -281,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_kernel(Params p) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     if (!ok && p.error != nullptr) atomicExch(p.error, 1);
-    if (warp == 4) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
 }
