@@ -30,12 +30,13 @@
 #include "mnk_dispatch.cuh"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace rn {
 constexpr int kC = 32;                        // tower channels
-constexpr int kBlocksM = 8;                   // UMMA M-blocks per CTA
+constexpr int kBlocksM = 4;                   // UMMA M-blocks per CTA (two CTAs per SM: one's epilogue overlaps the other's MMAs)
 constexpr int kRows = 128 * kBlocksM;         // pixel rows per CTA tile
-constexpr int kMargin = 40;                   // zero rows before/after the tile (>= n+2 for n <= 32, multiple of 8)
+constexpr int kMargin = 24;                   // zero rows before/after the tile (>= n+2, i.e. n <= 22; multiple of 8)
 constexpr int kBufRows = kRows + 2 * kMargin; // rows per activation buffer
 constexpr int kChunks = kC / 8;               // 16-byte k-chunks per row
 constexpr int kActBytes = kChunks * kBufRows * 16;
@@ -56,6 +57,7 @@ struct Smem {
     float head_b[4];
     alignas(8) unsigned long long mma_bar[kBlocksM];
     alignas(8) unsigned long long wts_bar[2];
+    float head_part[128][3];                  // last layer: partial head dot products of the upper channel half
     unsigned int tmem_base;
 };
 
@@ -140,6 +142,7 @@ struct Params {
     float* policy_feat;               // f32 [num_envs][2*cells]
     float* value_feat;                // f32 [num_envs][cells]
     int* error;                       // set to 1 on an mbarrier timeout
+    int debug_noshift;                // timing experiment only (MNK_TOWER_DEBUG_NOSHIFT=1): all taps read unshifted rows
 };
 
 MNK_DEV void tmem_ld16(u32 taddr, u32 (&v)[16]) {
@@ -191,7 +194,7 @@ MNK_DEV void epilogue_row(Smem& sm, const u32* acc, const float* bias, int out_b
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) resnet_tower_kernel(Params p) {
+__global__ void __launch_bounds__(kThreads, 2) resnet_tower_kernel(Params p) {
     extern __shared__ unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -278,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_kernel(Params p) {
             for (int g = 0; g < kGroups; ++g) {
                 u32 acc = 0;
                 for (int tap = 0; tap < kTaps; ++tap) {
-                    const int off = (tap / 3 - 1) * p.pw + (tap % 3 - 1);
+                    const int off = p.debug_noshift ? 0 : (tap / 3 - 1) * p.pw + (tap % 3 - 1);
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const u64 b_desc = umma_desc(w_base + (u32)((tap * kChunks + 2 * ks) * kC) * 16, kC * 16, 128);
                         const u32 a_addr0 = a_base + (u32)(2 * ks) * (kBufRows * 16) + (u32)(kMargin + 128 * g * kGroupBlocks + off) * 16;
@@ -309,19 +312,25 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_kernel(Params p) {
                     float v[16];
                     tmem_ld16(tmem_base + ((u32)(quarter * 32) << 16) + 32 * j + 16 * half, acc);
                     epilogue_row<16>(sm, acc, bias, out_buf, i, 16 * half, skip, valid, true, v);
-                } else if (half == 0) {   // last layer: full rows, then the 1x1 convolutions that open the two heads
-                    u32 acc[32];
-                    float v[32];
-                    tmem_ld32(tmem_base + ((u32)(quarter * 32) << 16) + 32 * j, acc);
-                    epilogue_row<32>(sm, acc, bias, out_buf, i, 0, skip, valid, false, v);
-                    if (valid) {
-                        float h0 = sm.head_b[0], h1 = sm.head_b[1], h2 = sm.head_b[2];
+                } else {   // last layer: no store; the 1x1 convolutions that open the two heads, from fp32 registers
+                    u32 acc[16];
+                    float v[16];
+                    tmem_ld16(tmem_base + ((u32)(quarter * 32) << 16) + 32 * j + 16 * half, acc);
+                    epilogue_row<16>(sm, acc, bias, out_buf, i, 16 * half, skip, valid, false, v);
+                    float h0 = 0.f, h1 = 0.f, h2 = 0.f;
 #pragma unroll
-                        for (int ch = 0; ch < 32; ++ch) {
-                            h0 = fmaf(v[ch], sm.head_w[0][ch], h0);
-                            h1 = fmaf(v[ch], sm.head_w[1][ch], h1);
-                            h2 = fmaf(v[ch], sm.head_w[2][ch], h2);
-                        }
+                    for (int ch = 0; ch < 16; ++ch) {
+                        h0 = fmaf(v[ch], sm.head_w[0][16 * half + ch], h0);
+                        h1 = fmaf(v[ch], sm.head_w[1][16 * half + ch], h1);
+                        h2 = fmaf(v[ch], sm.head_w[2][16 * half + ch], h2);
+                    }
+                    float* part = sm.head_part[quarter * 32 + lane];
+                    if (half == 1) { part[0] = h0; part[1] = h1; part[2] = h2; }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
+                    if (half == 0 && valid) {
+                        h0 += part[0] + sm.head_b[0];
+                        h1 += part[1] + sm.head_b[1];
+                        h2 += part[2] + sm.head_b[2];
                         const int s = i / p.rs, q = i - s * p.rs;
                         const int r = q / p.pw, c = q - r * p.pw;
                         const long long e = env0 + s;
@@ -330,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_kernel(Params p) {
                         p.policy_feat[(size_t)e * 2 * cells + cells + cell] = h1;
                         p.value_feat[(size_t)e * cells + cell] = h2;
                     }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
             }
         }
@@ -364,6 +374,7 @@ extern "C" int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, cons
     p.bits = reinterpret_cast<const u64*>(st->bits);
     p.swap = swap; p.weights = static_cast<const unsigned char*>(weights); p.bias = bias;
     p.head_w = head_w; p.head_b = head_b; p.policy_feat = policy_feat; p.value_feat = value_feat; p.error = error;
+    p.debug_noshift = getenv("MNK_TOWER_DEBUG_NOSHIFT") != nullptr;
     const size_t smem = sizeof(rn::Smem) + 128;
     static bool configured = false;
     if (!configured) {
