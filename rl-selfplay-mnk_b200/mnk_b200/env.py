@@ -148,6 +148,13 @@ class TorchVectorMnkEnv:
         self._call(self._L.mnk_observe, _ptr(obs), _ptr(mask), _ptr(swap), int(fix_all_masked))
         return {"observation": obs, "action_mask": mask}
 
+    def legal_mask(self, fix_all_masked: bool = False) -> torch.Tensor:
+        """bool[N, m*n] legal-cell mask only (no f32 observation): 1/9 of observe()'s bytes."""
+        self._fold_mirrors()
+        mask = torch.empty((self.num_envs, self.m * self.n), dtype=torch.bool, device=self._dev)
+        self._call(self._L.mnk_observe, None, _ptr(mask), None, int(fix_all_masked))
+        return mask
+
     def observe(self) -> Dict[str, torch.Tensor]:
         """reference :46-53 -- fresh tensors every call (callers mutate them)."""
         self._fold_mirrors()

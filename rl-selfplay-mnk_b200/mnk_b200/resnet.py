@@ -128,6 +128,14 @@ class NativeNNPolicy(Policy):
         self.seed = seed
         self._calls = 0
 
+    def act_from_env(self, env, counter: int, deterministic: bool = False) -> torch.Tensor:
+        """Action for the side to move of every env, straight from the bitboards (the wrapper's dense
+        opponent call): canonical view = planes swapped where the mover is white."""
+        swap = (env._meta & 1).to(torch.uint8)
+        logits, _ = self.net.forward_env(env, swap)
+        return masked_sample(logits, env.legal_mask(), seed=self.seed, counter=counter, row_offset=env.env_offset,
+                             deterministic=deterministic, want_log_prob=False)[0]
+
     def act(self, obs, deterministic: bool = False) -> torch.Tensor:
         dist, _ = self.net.forward(obs["observation"], obs["action_mask"])
         self._calls += 1

@@ -197,11 +197,30 @@ class RolloutCollector:
         start = time.time()
         if self._last_obs is None:                        # ppo.py:81-84: reset once, then carry obs across calls
             self._last_obs, _ = vec_env.reset()
+        elif self._last_obs["observation"] is None:       # previous rollout ran on the bitboard-fed path
+            self._last_obs = vec_env.get_agent_obs()
         obs = self._last_obs
         totals = torch.zeros(6, dtype=torch.float64, device=self._dev)
         steps = buffer.n_steps if n_steps is None else n_steps
         packed_fast_path = hasattr(vec_env, "_side") and hasattr(buffer, "store_obs_from")
+        native = packed_fast_path and hasattr(network, "forward_env")     # tcgen05 forward fed from bitboards
         for _ in range(steps):
+            if native:
+                env = vec_env.env
+                with torch.no_grad():
+                    logits, values = network.forward_env(env, swap=vec_env._side)
+                    self._calls += 1
+                    actions, log_probs, _ = masked_sample(logits, env.legal_mask(fix_all_masked=True), seed=self.seed,
+                                                          counter=self._calls, row_offset=self.row_offset)
+                buffer.store_obs_from(vec_env)
+                _, rewards, terminateds, truncateds, _ = vec_env.step(actions, materialise=False)
+                dones = terminateds | truncateds
+                buffer.add_transition(actions, rewards, values, log_probs, dones)
+                with torch.cuda.device(self._dev):
+                    check(self._L.mnk_episode_stats(_ptr(rewards), _ptr(dones), self.num_envs, _ptr(self._ep_reward),
+                                                     _ptr(self._ep_len), _ptr(totals),
+                                                     torch.cuda.current_stream(self._dev).cuda_stream), "mnk_episode_stats")
+                continue
             observation, action_mask = obs["observation"], obs["action_mask"]
             with torch.no_grad():                          # ppo.py:97-100
                 dist, values = network(observation, action_mask)
@@ -225,7 +244,7 @@ class RolloutCollector:
                                                  _ptr(self._ep_len), _ptr(totals),
                                                  torch.cuda.current_stream(self._dev).cuda_stream), "mnk_episode_stats")
             obs = next_obs
-        self._last_obs = obs
+        self._last_obs = obs if not native else {"observation": None, "action_mask": None}
         if self.world_size > 1:                            # the only collective of the rollout path
             import torch.distributed as dist_mod
             dist_mod.all_reduce(totals, op=dist_mod.ReduceOp.SUM, group=self.group)

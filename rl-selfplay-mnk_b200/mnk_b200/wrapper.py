@@ -70,7 +70,8 @@ class TorchSelfPlayWrapper:
         n = self.num_envs
         return (torch.empty(n, dtype=torch.float32, device=self._dev), torch.empty(n, dtype=torch.bool, device=self._dev))
 
-    def _run(self, actions: Optional[torch.Tensor], forced: Optional[torch.Tensor], reset_all: bool):
+    def _run(self, actions: Optional[torch.Tensor], forced: Optional[torch.Tensor], reset_all: bool,
+             materialise: bool = True):
         env = self.env
         env._fold_mirrors()
         flags = _lib.SP_RESET_ALL if reset_all else 0
@@ -87,7 +88,7 @@ class TorchSelfPlayWrapper:
         if forced is not None:
             forced = torch.as_tensor(forced, device=self._dev).to(torch.long).expand(self.num_envs).contiguous()
         rewards, terminated = self._new_out()
-        obs, mask = env._new_obs()
+        obs, mask = env._new_obs() if materialise else (None, None)
         self._steps += 1
         opp = self.opponent_policy
         with torch.cuda.device(self._dev):
@@ -98,12 +99,16 @@ class TorchSelfPlayWrapper:
             else:
                 if opp is None:
                     raise RuntimeError("TorchSelfPlayWrapper: set_opponent() has not been called")
-                opp_obs, opp_mask = env._new_obs()
+                from_bits = hasattr(opp, "act_from_env")     # native policies read the bitboards: no f32 opponent view
+                opp_obs, opp_mask = (None, None) if from_bits else env._new_obs()
                 check(self._L.mnk_selfplay_agent(env._stp, self._spp, _ptr(a), _ptr(forced), _ptr(rewards),
                                                   _ptr(terminated), _ptr(self._opp_active), _ptr(opp_obs), _ptr(opp_mask),
                                                   flags, self._stream()), "mnk_selfplay_agent")
-                with torch.no_grad():      # reference :91-94: one positional argument
-                    opp_actions = opp.act({"observation": opp_obs, "action_mask": opp_mask})
+                with torch.no_grad():
+                    if from_bits:
+                        opp_actions = opp.act_from_env(env, self._steps)
+                    else:                  # reference :91-94: one positional argument
+                        opp_actions = opp.act({"observation": opp_obs, "action_mask": opp_mask})
                 oa = torch.as_tensor(opp_actions, device=self._dev)
                 oflags = 0
                 if oa.dtype == torch.int32:
@@ -120,20 +125,21 @@ class TorchSelfPlayWrapper:
         return {"observation": obs, "action_mask": mask}, rewards, terminated
 
     # ------------------------------------------------------------------ reference methods
-    def reset(self, seed=None, options=None):
+    def reset(self, seed=None, options=None, materialise: bool = True):
         """reference :19-30 (``seed`` is ignored there too)."""
         forced = None
         if options and "agent_side" in options:
             forced = options["agent_side"]
         elif self.next_sides is not None:
             forced = self.next_sides
-        obs, _, _ = self._run(None, forced, reset_all=True)
+        obs, _, _ = self._run(None, forced, reset_all=True, materialise=materialise)
         self.pending_resets.zero_()     # no-op by construction; mirrors :21
         return obs, {}
 
-    def step(self, actions: torch.Tensor):
-        """reference :32-67"""
-        obs, rewards, terminated = self._run(actions, self.next_sides, reset_all=False)
+    def step(self, actions: torch.Tensor, materialise: bool = True):
+        """reference :32-67.  materialise=False skips writing the f32 observation / bool mask (callers that
+        read the bitboards, e.g. the tcgen05 forward): obs entries are then None."""
+        obs, rewards, terminated = self._run(actions, self.next_sides, reset_all=False, materialise=materialise)
         return obs, rewards, terminated, torch.zeros_like(terminated), {}
 
     def get_agent_obs(self) -> Dict[str, torch.Tensor]:

@@ -89,3 +89,50 @@ def test_native_nn_policy_in_wrapper():
         done += int(term.sum())
     pol.net.check_error()
     assert done > 100
+
+
+def test_native_rollout_matches_generic_rollout_path():
+    """RolloutCollector on the bitboard-fed path (tcgen05 forward, no f32 observation anywhere) stores the
+    same observations / actions / rewards as the generic path driven by the same NativeResNet through
+    its module-compatible forward(obs, mask) -- same seeds, same Philox counters."""
+    from mnk_b200 import (NativeNNPolicy, NativeResNet, ResNetActorCritic, RolloutBuffer, RolloutCollector,
+                          TorchSelfPlayWrapper, TorchVectorMnkEnv)
+    torch.manual_seed(5)
+    net = ResNetActorCritic((2, 9, 9), 81).to(DEV).eval()
+    with torch.no_grad():
+        net.policy_head[7].weight.mul_(50.0)
+    opp_net = ResNetActorCritic((2, 9, 9), 81).to(DEV).eval()
+    ne, steps = 700, 24
+    runs = []
+    for native_path in (True, False):
+        env = TorchVectorMnkEnv(9, 9, 5, ne, device=DEV)
+        wr = TorchSelfPlayWrapper(env, seed=9)
+        opp = NativeNNPolicy(opp_net, device=DEV, seed=4)
+        if not native_path:
+            class ObsOnly:          # hide act_from_env: forces the f32 opponent view + forward(obs, mask)
+                def __init__(self, inner): self.inner = inner; self.calls = 0
+                def act(self, obs):
+                    self.calls += 1
+                    dist, _ = self.inner.net.forward(obs["observation"], obs["action_mask"])
+                    from mnk_b200 import masked_sample
+                    return masked_sample(dist._raw, dist._mask, seed=self.inner.seed, counter=wr._steps, want_log_prob=False)[0]
+            wr.set_opponent(ObsOnly(opp))
+        else:
+            wr.set_opponent(opp)
+        agent = NativeResNet(net, device=DEV)
+        buf = RolloutBuffer(steps, ne, (2, 9, 9), 81, device=DEV, k=5)
+        col = RolloutCollector(ne, device=DEV, seed=21)
+        if native_path:
+            wr.reset(materialise=False)
+            col._last_obs = {"observation": None, "action_mask": None}
+            stats = col.collect(agent, wr, buf)
+        else:
+            stats = col.collect(agent.forward, wr, buf)
+        agent.check_error()
+        runs.append((buf.observations.clone(), buf.actions.clone(), buf.rewards.clone(), buf.dones.clone(),
+                     buf.log_probs.clone(), buf.values.clone(), stats))
+    a, b = runs
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)
+    assert torch.allclose(a[4], b[4], atol=1e-6) and torch.allclose(a[5], b[5], atol=1e-6)
+    assert a[6].episodes == b[6].episodes > 0 and a[6].wins == b[6].wins
