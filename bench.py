@@ -42,19 +42,37 @@ for p in (PKG, ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-M, N_COLS, K_LINE = 9, 9, 5
-ENVS_PER_GPU = 65536
-CELLS = M * N_COLS
-STATE_BYTES = 2 * 8 * 2 + 4                       # two planes x two u64 words + meta
-ALG_BYTES_PER_ENV_STEP = 8 + 2 * STATE_BYTES + 8 * CELLS + CELLS + 5   # = 814
 METRIC = "env steps/sec (9x9x5, win-check)"
 UNIT = "env-steps/s"
 MIX_PLIES = 64
 L2_BYTES = 126 * 1024 * 1024
 
+# name -> (m, n, k, envs per GPU at N GPUs, BASELINE.json config it stands for)
+WORKLOADS = {
+    "cfg2": (9, 9, 5, lambda n: 65536, "cfg2: gomoku 9x9x5, 65536 envs/GPU", "weak"),
+    "cfg4": (13, 13, 5, lambda n: 1048576 // n, "cfg4: 13x13x5, 1,048,576 envs sharded over the GPUs", "strong"),
+    "cfg5": (19, 19, 5, lambda n: 4194304 // 8, "cfg5: 19x19x5, 524,288 envs/GPU (4,194,304 over 8 GPUs)", "weak"),
+}
+SCALING = "weak"
+M = N_COLS = K_LINE = CELLS = ENVS_PER_GPU = ALG_BYTES_PER_ENV_STEP = 0
+WORKLOAD_DESC = ""
+
+
+def configure(name: str, gpus: int, envs_override=None):
+    """Sets the board geometry, per-GPU env count and the algorithmic bytes per env-step (SURVEY 8d:
+    8 B action + 2 x packed state + f32 observation + bool mask + reward/done)."""
+    global M, N_COLS, K_LINE, CELLS, ENVS_PER_GPU, ALG_BYTES_PER_ENV_STEP, WORKLOAD_DESC, METRIC, SCALING
+    M, N_COLS, K_LINE, envs_fn, WORKLOAD_DESC, SCALING = WORKLOADS[name]
+    CELLS = M * N_COLS
+    ENVS_PER_GPU = envs_override or envs_fn(gpus)
+    words = (M * (N_COLS + 1) + 63) // 64
+    state_bytes = 2 * 8 * words + 4
+    ALG_BYTES_PER_ENV_STEP = 8 + 2 * state_bytes + 8 * CELLS + CELLS + 5      # 814 at 9x9
+    METRIC = f"env steps/sec ({M}x{N_COLS}x{K_LINE}, win-check)"
+
 
 def workload_name(envs):
-    return (f"cfg2: gomoku 9x9x5, {envs} envs/GPU, seeded random legal actions, env.step (placement + "
+    return (f"{WORKLOAD_DESC} ({envs} envs on this GPU), seeded random legal actions, env.step (placement + "
             "k-in-a-row win/draw check + rewards/dones + f32 obs & bool mask materialised) + auto-reset")
 
 
@@ -340,7 +358,7 @@ def run_b200_arm(args):
         achieved = ALG_BYTES_PER_ENV_STEP * envs / (launch_us * 1e-6) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {
                 "workload": workload_name(envs), "envs_per_gpu": envs, "global_envs": total_envs,
@@ -352,7 +370,7 @@ def run_b200_arm(args):
             },
             "verified_state_digest": verified,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": profiled_traffic(), "kernel": "step_dense_kernel<SGeom<9,9,5>>",
+                         "traffic": profiled_traffic() if (M, N_COLS) == (9, 9) and envs == 65536 else None, "kernel": f"step_dense_kernel<SGeom<{M},{N_COLS},{K_LINE}>>",
                          "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP, "launch_us": launch_us, "peak_source": peak_src},
             "e2e": {"value": total_envs * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * envs,
                     "d2h_bytes_per_step": 5 * envs, "steps": e2e_steps,
@@ -388,19 +406,122 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------
+# cfg3: self-play rollout with the policy/value network (secondary workload, --workload cfg3)
+# ------------------------------------------------------------------------------------------------
+def run_rollout_arm(args):
+    """BASELINE cfg3 per GPU: 9x9x5, agent and opponent both resnet_b_s (same random-init weights, opponent
+    frozen), tcgen05 forward fed from bitboards, Gumbel-max sampling, fused wrapper, packed PPO buffer, on-device
+    episode statistics; K rollout steps timed.  Metric = the reference's fps (ppo.py:126-129): agent steps / s."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    from mnk_b200 import (NativeNNPolicy, NativeResNet, ResNetActorCritic, RolloutBuffer, RolloutCollector,
+                          TorchSelfPlayWrapper, TorchVectorMnkEnv)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    envs, K, W = args.envs, args.steps, args.warmup
+    torch.manual_seed(0)
+    net = ResNetActorCritic((2, M, N_COLS), CELLS).to(dev).eval()
+    agent = NativeResNet(net, device=dev)
+    opponent = NativeNNPolicy(copy.deepcopy(net), device=dev, seed=7)
+    env = TorchVectorMnkEnv(M, N_COLS, K_LINE, envs, device=f"cuda:{local_rank}", env_offset=rank * envs)
+    wr = TorchSelfPlayWrapper(env, seed=20261018)
+    wr.set_opponent(opponent)
+    col = RolloutCollector(envs, device=dev, seed=11, row_offset=rank * envs, world_size=world)
+    wr.reset(materialise=False)
+    col._last_obs = {"observation": None, "action_mask": None}
+    warm_buf = RolloutBuffer(max(W, MIX_PLIES // 2), envs, (2, M, N_COLS), CELLS, device=dev, k=K_LINE)
+    col.collect(agent, wr, warm_buf)                       # warm-up: also brings games to a stationary depth mix
+    buf = RolloutBuffer(K, envs, (2, M, N_COLS), CELLS, device=dev, k=K_LINE)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    stats = col.collect(agent, wr, buf)                    # K steps; ends with the NCCL all-reduce + one host read
+    ev1.record()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    agent.check_error()
+    opponent.net.check_error()
+    times = torch.tensor([ms, wall_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, wall_ms = (float(x) for x in times.tolist())
+    if rank == 0:
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peak, peak_src = float(json.load(f)["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained"
+        except Exception:
+            peak, peak_src = 1400.0, "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        flop_per_agent_step = 2 * 12.136e6                 # agent + opponent forward (SURVEY 8d)
+        total = envs * world * K
+        value = total / (ms * 1e-3)
+        achieved = value * flop_per_agent_step / 1e12
+        line = {
+            "metric": "self-play rollout steps/sec (9x9x5, resnet_b_s agent + opponent)", "value": value, "unit": "agent-steps/s",
+            "n_gpus": world, "steps": K, "warmup": warm_buf.n_steps, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"cfg3: gomoku 9x9x5 self-play rollout, {envs} envs/GPU x {K} steps, resnet_b_s agent + frozen "
+                                   "copy as opponent (random-init weights), tcgen05 forward from bitboards, Gumbel-max sampling, "
+                                   "fused wrapper, packed PPO buffer, on-device episode stats",
+                       "envs_per_gpu": envs, "global_envs": envs * world,
+                       "l2": f"per step the towers stream {envs * 72 / 2**20:.1f} MiB of bitboards and {envs * 972 * 2 / 2**20:.0f} MiB of "
+                             "head features; rollout buffer slots are distinct per step",
+                       "parallelism": f"env-shard x{world}, one NCCL all-reduce of 6 doubles per rollout"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "resnet_tower_kernel (2 launches per agent-step)",
+                         "flop_per_agent_step": flop_per_agent_step, "peak_source": peak_src},
+            "e2e": {"value": total / (wall_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 48.0 / K,
+                    "api": "RolloutCollector.collect (wall clock incl. the statistics all-reduce and host read)"},
+            "gpu_launches": 10 * K,
+            "clocks": clocks,
+            "stats": {"episodes": stats.episodes, "mean_reward": stats.mean_reward, "mean_length": stats.mean_length,
+                      "wins": stats.wins, "losses": stats.losses, "draws": stats.draws},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + ["cfg3"],
+                    help="cfg2 (default, the headline), cfg4 / cfg5 (larger boards), cfg3 (self-play rollout with the network)")
+    ap.add_argument("--envs", type=int, default=None, help="envs per GPU (default: the workload's)")
     ap.add_argument("--e2e-steps", type=int, default=500)
     ap.add_argument("--cpu-steps", type=int, default=60)
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload == "cfg3":
+        configure("cfg2", args.gpus, args.envs or 32768)
+        args.envs = ENVS_PER_GPU
+        return run_rollout_arm(args)
+    configure(args.workload, args.gpus, args.envs)
+    args.envs = ENVS_PER_GPU
     if args.impl == "reference":
         run_reference_arm(args)
     else:
