@@ -218,6 +218,24 @@ int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, const void* wei
                      const float* head_w, const float* head_b, int32_t blocks, float* policy_feat,
                      float* value_feat, int32_t* error, void* stream);
 
+/* The heads' tails after the tower (resnet.py:41-63), one kernel, fp32:
+ *   logits = Linear(128,A)(ReLU(LN(128)(Linear(2A,128)(ReLU(LN(2A)(policy_feat))))))
+ *   values = Tanh(Linear(128,1)(ReLU(LN(128)(Linear(A,128)(ReLU(LN(A)(value_feat)))))))
+ * Linear weights are passed TRANSPOSED ([in][out], contiguous); hidden width is 128. */
+typedef struct mnk_heads_weights {
+    const float *p_ln1_w, *p_ln1_b; /* [2A]                         */
+    const float *p_w1t, *p_b1;      /* [2A][128], [128]             */
+    const float *p_ln2_w, *p_ln2_b; /* [128]                        */
+    const float *p_w2t, *p_b2;      /* [128][A], [A]                */
+    const float *v_ln1_w, *v_ln1_b; /* [A]                          */
+    const float *v_w1t, *v_b1;      /* [A][128], [128]              */
+    const float *v_ln2_w, *v_ln2_b; /* [128]                        */
+    const float *v_w2, *v_b2;       /* [128], [1]                   */
+} mnk_heads_weights_t;
+
+int mnk_resnet_heads(const float* policy_feat, const float* value_feat, int64_t rows, int32_t cells,
+                     const mnk_heads_weights_t* w, float* logits, float* values, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

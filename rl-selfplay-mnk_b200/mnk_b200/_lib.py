@@ -38,6 +38,13 @@ class MnkSelfplay(ctypes.Structure):
                 ("seed", ctypes.c_uint64), ("env_offset", ctypes.c_int64)]
 
 
+class MnkHeadsWeights(ctypes.Structure):
+    """struct mnk_heads_weights of include/mnk_b200.h (16 device pointers)."""
+    NAMES = ("p_ln1_w", "p_ln1_b", "p_w1t", "p_b1", "p_ln2_w", "p_ln2_b", "p_w2t", "p_b2",
+             "v_ln1_w", "v_ln1_b", "v_w1t", "v_b1", "v_ln2_w", "v_ln2_b", "v_w2", "v_b2")
+    _fields_ = [(n, ctypes.c_void_p) for n in NAMES]
+
+
 SP_ACTIONS_I32, SP_RESET_ALL, SP_DETERMINISTIC_OPP = 1, 2, 4
 
 
@@ -107,6 +114,7 @@ SIGNATURES = {
     "mnk_gae": (_I32, [_VP, _VP, _VP, _VP, _I64, _I64, ctypes.c_float, ctypes.c_float, _VP, _VP, _VP]),
     "mnk_episode_stats": (_I32, [_VP, _VP, _I64, _VP, _VP, _VP, _VP]),
     "mnk_resnet_tower": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
+    "mnk_resnet_heads": (_I32, [_VP, _VP, _I64, _I32, ctypes.POINTER(MnkHeadsWeights), _VP, _VP, _VP]),
 }
 
 

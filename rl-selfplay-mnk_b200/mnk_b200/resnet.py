@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import MnkState, check
+from ._lib import MnkHeadsWeights, MnkState, check
 from .policy import Policy
 from .sampling import MaskedCategorical, masked_sample
 
@@ -40,7 +40,8 @@ def _arrange(w: torch.Tensor) -> torch.Tensor:
 
 
 class NativeResNet:
-    def __init__(self, model: nn.Module, device="cuda"):
+    def __init__(self, model: nn.Module, device="cuda", torch_heads: bool = False):
+        self.torch_heads = torch_heads      # run the head tails through the original torch modules (debug / comparison)
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("mnk_b200.NativeResNet: CUDA only (no CPU fallback)")
@@ -69,6 +70,32 @@ class NativeResNet:
         self.policy_tail = nn.Sequential(*list(model.policy_head)[2:]).to(dev).eval()        # LN, ReLU, Linear, LN, ReLU, Linear
         self.value_tail = nn.Sequential(*list(model.value_head)[2:]).to(dev).eval()          # ... + Tanh
         self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        # fused heads kernel (mnk_resnet_heads): LN / Linear parameters, Linear weights transposed to [in][out]
+        ph, vh = model.policy_head, model.value_head
+        if ph[4].out_features != 128 or vh[4].out_features != 128:
+            raise ValueError("NativeResNet supports head_hidden_dim = 128 (resnet_b_s)")
+        f = lambda t: t.detach().float().to(dev).contiguous()
+        self._head_tensors = {
+            "p_ln1_w": f(ph[2].weight), "p_ln1_b": f(ph[2].bias), "p_w1t": f(ph[4].weight.t()), "p_b1": f(ph[4].bias),
+            "p_ln2_w": f(ph[5].weight), "p_ln2_b": f(ph[5].bias), "p_w2t": f(ph[7].weight.t()), "p_b2": f(ph[7].bias),
+            "v_ln1_w": f(vh[2].weight), "v_ln1_b": f(vh[2].bias), "v_w1t": f(vh[4].weight.t()), "v_b1": f(vh[4].bias),
+            "v_ln2_w": f(vh[5].weight), "v_ln2_b": f(vh[5].bias), "v_w2": f(vh[7].weight.reshape(-1)), "v_b2": f(vh[7].bias),
+        }
+        self._heads = MnkHeadsWeights(*[self._head_tensors[n].data_ptr() for n in MnkHeadsWeights.NAMES])
+
+    @torch.no_grad()
+    def tails(self, pf: torch.Tensor, vf: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """logits f32[N, A], value f32[N, 1] from the tower's head features."""
+        if self.torch_heads:
+            return self.policy_tail(pf), self.value_tail(vf)
+        rows, cells = vf.shape
+        logits = torch.empty((rows, cells), dtype=torch.float32, device=self._dev)
+        values = torch.empty((rows, 1), dtype=torch.float32, device=self._dev)
+        with torch.cuda.device(self._dev):
+            check(self._L.mnk_resnet_heads(pf.data_ptr(), vf.data_ptr(), rows, cells, ctypes.byref(self._heads),
+                                            logits.data_ptr(), values.data_ptr(),
+                                            torch.cuda.current_stream(self._dev).cuda_stream), "mnk_resnet_heads")
+        return logits, values
 
     @torch.no_grad()
     def features(self, state: MnkState, num_envs: int, cells: int, swap: Optional[torch.Tensor]):
@@ -88,7 +115,7 @@ class NativeResNet:
         bitboards; `swap` u8[N] != 0 exchanges the planes (the canonical view of a white mover/agent)."""
         env._fold_mirrors()
         pf, vf = self.features(env._st, env.num_envs, env.m * env.n, swap)
-        return self.policy_tail(pf), self.value_tail(vf)
+        return self.tails(pf, vf)
 
     @torch.no_grad()
     def forward(self, obs: torch.Tensor, action_mask: Optional[torch.Tensor] = None):
@@ -106,7 +133,7 @@ class NativeResNet:
             check(self._L.mnk_pack_boards(ctypes.byref(st), obs.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream),
                   "mnk_pack_boards")
         pf, vf = self.features(st, b, m * n, None)
-        logits, value = self.policy_tail(pf), self.value_tail(vf)
+        logits, value = self.tails(pf, vf)
         if action_mask is not None and action_mask.dim() == 1:
             action_mask = action_mask.unsqueeze(0)
         return MaskedCategorical(logits, action_mask), value

@@ -136,3 +136,31 @@ def test_native_rollout_matches_generic_rollout_path():
         assert torch.equal(x, y)
     assert torch.allclose(a[4], b[4], atol=1e-6) and torch.allclose(a[5], b[5], atol=1e-6)
     assert a[6].episodes == b[6].episodes > 0 and a[6].wins == b[6].wins
+
+
+@pytest.mark.parametrize("m,n", [(9, 9), (13, 13), (19, 19), (5, 7)], ids=lambda v: str(v))
+def test_fused_heads_match_torch_modules(m, n):
+    """mnk_resnet_heads (LN -> ReLU -> Linear -> LN -> ReLU -> Linear [-> Tanh], fp32) against the same torch
+    modules on the same tower features, including a row count that is not a multiple of the 8-sample batch."""
+    from mnk_b200 import NativeResNet, ResNetActorCritic
+    torch.manual_seed(7)
+    cells = m * n
+    net = ResNetActorCritic((2, m, n), cells).to(DEV).eval()
+    with torch.no_grad():
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.LayerNorm):
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.normal_(0, 0.3)
+            elif isinstance(mod, torch.nn.Linear):
+                mod.bias.normal_(0, 0.2)
+        net.policy_head[7].weight.mul_(40.0)
+    native = NativeResNet(net, device=DEV)
+    for rows in (1, 8, 13, 1001):
+        pf = torch.randn(rows, 2 * cells, device=DEV) * 2
+        vf = torch.randn(rows, cells, device=DEV) * 2
+        logits, values = native.tails(pf, vf)
+        with torch.no_grad():
+            want_l, want_v = native.policy_tail(pf), native.value_tail(vf)
+        assert logits.shape == want_l.shape and values.shape == want_v.shape
+        assert torch.allclose(logits, want_l, rtol=1e-4, atol=2e-4), (logits - want_l).abs().max()
+        assert torch.allclose(values, want_v, rtol=1e-4, atol=1e-5), (values - want_v).abs().max()
