@@ -49,6 +49,9 @@ extern "C" {
 #define MNK_STEP_ACTIONS_I32 1u /* `actions` is int32_t[] instead of int64_t[]                      */
 #define MNK_STEP_AUTORESET 2u   /* envs that finish are reset after their outputs are written:       */
                                 /* equals env.step(a) followed by env.reset(dones.nonzero())        */
+#define MNK_STEP_ZEROCOPY 4u    /* mnk_step_host only: host_actions / host_rd are pinned, device-mapped */
+                                /* (UVA) buffers; the kernel reads / writes them over PCIe itself,   */
+                                /* no staging copies (dev_actions / dev_rd may be NULL)              */
 
 typedef struct mnk_state {
     int32_t m, n, k;
@@ -101,7 +104,9 @@ int mnk_step(const mnk_state_t* st, const void* actions, const int64_t* idx, int
  * tensors uses): copies host_actions to dev_actions, steps, copies rewards / dones back and
  * SYNCHRONISES the stream.  host_* should be pinned.  dev_* are caller-owned scratch:
  * dev_actions i64|i32[num_envs], dev_rd = 5 * num_envs bytes (f32 rewards then u8 dones);
- * host_rd receives the same 5 * num_envs bytes.  obs / mask stay on the device (may be NULL). */
+ * host_rd receives the same 5 * num_envs bytes.  obs / mask stay on the device (may be NULL).
+ * With MNK_STEP_ZEROCOPY the step kernel dereferences the pinned host buffers directly (one launch +
+ * one synchronise instead of copy + launch + copy + synchronise). */
 int mnk_step_host(const mnk_state_t* st, const void* host_actions, void* dev_actions, void* dev_rd,
                   void* host_rd, float* obs, uint8_t* mask, uint32_t flags, void* stream);
 

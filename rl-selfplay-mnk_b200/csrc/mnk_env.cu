@@ -303,9 +303,19 @@ int mnk_step(const mnk_state_t* st, const void* actions, const int64_t* idx, int
 int mnk_step_host(const mnk_state_t* st, const void* host_actions, void* dev_actions, void* dev_rd, void* host_rd,
                   float* obs, uint8_t* mask, uint32_t flags, void* stream) {
     if (int rc = mnk_check_state(st)) return rc;
-    if (host_actions == nullptr || dev_actions == nullptr || dev_rd == nullptr || host_rd == nullptr) return MNK_ERR_NULL;
+    if (host_actions == nullptr || host_rd == nullptr) return MNK_ERR_NULL;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = (size_t)st->num_envs;
+    if (flags & MNK_STEP_ZEROCOPY) {   // the kernel reads the pinned actions and writes rewards / dones over PCIe itself
+        float* rewards_h = static_cast<float*>(host_rd);
+        uint8_t* dones_h = static_cast<uint8_t*>(host_rd) + 4 * n;
+        const int rc = mnk_step(st, host_actions, nullptr, st->num_envs, rewards_h, dones_h, obs, mask, nullptr,
+                                flags & ~MNK_STEP_ZEROCOPY, stream);
+        if (rc != MNK_OK) return rc;
+        const cudaError_t e = cudaStreamSynchronize(s);
+        return e == cudaSuccess ? MNK_OK : (int)e;
+    }
+    if (dev_actions == nullptr || dev_rd == nullptr) return MNK_ERR_NULL;
     const size_t abytes = n * ((flags & MNK_STEP_ACTIONS_I32) ? 4 : 8);
     cudaError_t e = cudaMemcpyAsync(dev_actions, host_actions, abytes, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return (int)e;

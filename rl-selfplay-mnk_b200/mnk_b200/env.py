@@ -238,15 +238,21 @@ class TorchVectorMnkEnv:
         return out
 
     def step_host(self, host_actions: torch.Tensor, host_out: torch.Tensor, autoreset: bool = False,
-                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, zero_copy: bool = False):
         """End-to-end step for callers holding HOST buffers: pinned int64 actions in, pinned
         rewards/dones bytes out (5*N bytes: f32 rewards then u8 dones), one H2D + launch + D2H +
-        stream sync inside libmnk_b200 (mnk_step_host).  Observation / mask stay on the device."""
+        stream sync inside libmnk_b200 (mnk_step_host).  Observation / mask stay on the device.
+        zero_copy=True: both host buffers must be pinned (torch .pin_memory()); the kernel then reads the
+        actions and writes rewards / dones over PCIe itself -- one launch + one sync, no staging copies."""
         self._fold_mirrors()
         if not hasattr(self, "_dev_actions"):
             self._dev_actions = torch.empty(self.num_envs, dtype=torch.long, device=self._dev)
             self._dev_rd = torch.empty(5 * self.num_envs, dtype=torch.uint8, device=self._dev)
         flags = _lib.STEP_AUTORESET if autoreset else 0
+        if zero_copy:
+            if not (host_actions.is_pinned() and host_out.is_pinned()):
+                raise ValueError("step_host(zero_copy=True) needs pinned host tensors")
+            flags |= _lib.STEP_ZEROCOPY
         if host_actions.dtype == torch.int32:
             flags |= _lib.STEP_ACTIONS_I32
         obs, mask = out if out is not None else self._new_obs()

@@ -218,7 +218,7 @@ def test_host_step_path():
     for step in range(30):
         a = twin.random_legal_actions(5, step)
         host_a.copy_(a)
-        obs, r, d = env.step_host(host_a, host_out, autoreset=True)
+        obs, r, d = env.step_host(host_a, host_out, autoreset=True, zero_copy=(step % 2 == 1))
         o2, r2, d2 = twin.step_autoreset(a)
         assert not r.is_cuda and torch.equal(r, r2.cpu()) and torch.equal(d, d2.cpu())
         assert torch.equal(obs["observation"], o2["observation"])
