@@ -266,7 +266,7 @@ def run_b200_arm(args):
     rewards = torch.empty(envs, dtype=torch.float32, device=dev)
     dones = torch.empty(envs, dtype=torch.bool, device=dev)
     L = _lib.lib()
-    flags = _lib.STEP_AUTORESET
+    flags = _lib.STEP_AUTORESET | (0 if args.no_pdl else _lib.STEP_PDL)
 
     def launch(t, stream):
         rc = L.mnk_step(env._stp, actions[t].data_ptr(), None, envs, rewards.data_ptr(), dones.data_ptr(),
@@ -369,7 +369,7 @@ def run_b200_arm(args):
             "dtype": "u64", "data": "synthetic",
             "config": {
                 "workload": workload_name(envs), "envs_per_gpu": envs, "global_envs": total_envs,
-                "launch": f"one CUDA graph of {K} step_dense_kernel nodes (eager launches: "
+                "launch": f"one CUDA graph of {K} step_dense_kernel nodes{'' if args.no_pdl else ' with programmatic dependent launch edges'} (eager launches: "
                           f"{total_envs * K / (ms_eager * 1e-3):.4g} {UNIT})",
                 "l2": f"obs/mask outputs rotate through a ring of {ring} buffer sets "
                       f"({ring * per_set / 2**20:.0f} MiB > 126 MiB L2); inputs: {K} distinct action batches",
@@ -524,6 +524,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=60)
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="plain launches instead of programmatic dependent launch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.workload == "cfg3":

@@ -49,6 +49,8 @@ extern "C" {
 #define MNK_STEP_ACTIONS_I32 1u /* `actions` is int32_t[] instead of int64_t[]                      */
 #define MNK_STEP_AUTORESET 2u   /* envs that finish are reset after their outputs are written:       */
                                 /* equals env.step(a) followed by env.reset(dones.nonzero())        */
+#define MNK_STEP_PDL 8u         /* dense step only: launch with programmatic stream serialisation so that   */
+                                /* back-to-back steps on one stream overlap launch / drain (sm_90+ PDL)     */
 #define MNK_STEP_ZEROCOPY 4u    /* mnk_step_host only: host_actions / host_rd are pinned, device-mapped */
                                 /* (UVA) buffers; the kernel reads / writes them over PCIe itself,   */
                                 /* no staging copies (dev_actions / dev_rd may be NULL)              */

@@ -44,6 +44,11 @@ step_dense_kernel(G g, mnk_state_t st, const void* __restrict__ actions, float* 
     const int tile_envs = (int)min((long long)kTileEnvs, st.num_envs - e0);
     const bool emit = obs != nullptr || mask != nullptr;
     const bool stream = emit && tile_streams<G>(tile_envs, obs, mask);   // block-uniform
+    // Programmatic dependent launch (MNK_STEP_PDL): let the next step's CTAs become resident while this grid
+    // drains, and do not touch anything the previous step wrote before it has completed.  Both are no-ops
+    // for a plain launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     u64 obsd[G::NWD];
     u64 legd[G::NWL];
     if (threadIdx.x < 32) {   // the compute warp: lane L owns env e0 + L
@@ -273,11 +278,23 @@ int mnk_step(const mnk_state_t* st, const void* actions, const int64_t* idx, int
             const unsigned blocks = mnk_cta_tiles(st->num_envs);
             // no materialisation => only the compute warp has work: launch single-warp CTAs
             const int threads = (obs != nullptr || mask != nullptr) ? tile_cta_threads<G>() : 32;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(blocks);
+            cfg.blockDim = dim3(threads);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = (flags & MNK_STEP_PDL) ? 1 : 0;
+            const mnk_state_t stv = *st;
+            cudaError_t e;
             if (act32)
-                step_dense_kernel<G, true><<<blocks, threads, 0, s>>>(g, *st, actions, rewards, dones, obs, mask, illegal, flags);
+                e = cudaLaunchKernelEx(&cfg, step_dense_kernel<G, true>, g, stv, actions, rewards, dones, obs, mask, illegal, flags);
             else
-                step_dense_kernel<G, false><<<blocks, threads, 0, s>>>(g, *st, actions, rewards, dones, obs, mask, illegal, flags);
-            return mnk_launch_status();
+                e = cudaLaunchKernelEx(&cfg, step_dense_kernel<G, false>, g, stv, actions, rewards, dones, obs, mask, illegal, flags);
+            return e == cudaSuccess ? mnk_launch_status() : (int)e;
         });
     }
     // step_subset: full-size zeroed outputs, scattered update, then observe() over all envs
