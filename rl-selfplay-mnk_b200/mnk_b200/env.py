@@ -57,6 +57,8 @@ class TorchVectorMnkEnv:
         self._boards_mirror: Optional[torch.Tensor] = None
         self._player_mirror: Optional[torch.Tensor] = None
         self._count_mirror: Optional[torch.Tensor] = None
+        self._dev_actions = self._dev_rd = None     # staging buffers of step_host (non zero-copy transport)
+        self._host_views = {}
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -245,22 +247,29 @@ class TorchVectorMnkEnv:
         zero_copy=True: both host buffers must be pinned (torch .pin_memory()); the kernel then reads the
         actions and writes rewards / dones over PCIe itself -- one launch + one sync, no staging copies."""
         self._fold_mirrors()
-        if not hasattr(self, "_dev_actions"):
-            self._dev_actions = torch.empty(self.num_envs, dtype=torch.long, device=self._dev)
-            self._dev_rd = torch.empty(5 * self.num_envs, dtype=torch.uint8, device=self._dev)
+        n = self.num_envs
         flags = _lib.STEP_AUTORESET if autoreset else 0
         if zero_copy:
             if not (host_actions.is_pinned() and host_out.is_pinned()):
                 raise ValueError("step_host(zero_copy=True) needs pinned host tensors")
             flags |= _lib.STEP_ZEROCOPY
+            dev_actions = dev_rd = None
+        else:
+            if self._dev_actions is None:
+                self._dev_actions = torch.empty(n, dtype=torch.long, device=self._dev)
+                self._dev_rd = torch.empty(5 * n, dtype=torch.uint8, device=self._dev)
+            dev_actions, dev_rd = self._dev_actions.data_ptr(), self._dev_rd.data_ptr()
         if host_actions.dtype == torch.int32:
             flags |= _lib.STEP_ACTIONS_I32
         obs, mask = out if out is not None else self._new_obs()
-        self._call(self._L.mnk_step_host, _ptr(host_actions), _ptr(self._dev_actions), _ptr(self._dev_rd),
-                   _ptr(host_out), _ptr(obs), _ptr(mask), flags)
+        self._call(self._L.mnk_step_host, host_actions.data_ptr(), dev_actions, dev_rd, host_out.data_ptr(), _ptr(obs),
+                   _ptr(mask), flags)
         self._refresh_mirrors()
-        n = self.num_envs
-        return {"observation": obs, "action_mask": mask}, host_out[:4 * n].view(torch.float32), host_out[4 * n:].view(torch.bool)
+        views = self._host_views.get(host_out.data_ptr())
+        if views is None:       # typed views of the caller's byte buffer, built once per buffer
+            views = (host_out[:4 * n].view(torch.float32), host_out[4 * n:5 * n].view(torch.bool))
+            self._host_views = {host_out.data_ptr(): views}
+        return {"observation": obs, "action_mask": mask}, views[0], views[1]
 
     def state_checksum(self) -> int:
         """Order-sensitive 64-bit digest of the packed state (used by bench.py / tests)."""

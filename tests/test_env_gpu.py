@@ -223,3 +223,46 @@ def test_host_step_path():
         assert not r.is_cuda and torch.equal(r, r2.cpu()) and torch.equal(d, d2.cpu())
         assert torch.equal(obs["observation"], o2["observation"])
     assert env.state_checksum() == twin.state_checksum()
+
+
+def test_tournament_style_consumer_on_raw_env():
+    """Second consumer of the env in the reference: MatchRunner._play_batch_games
+    (src/model_comparison/match_runner.py:125-218) drives the RAW env -- reads env.current_player every
+    ply, builds per-side observation subsets, steps only unfinished games with step_subset.  Same loop
+    here on the drop-in and, in lock-step, on the CPU oracle with identical actions."""
+    m, n, k, games = 6, 7, 4, 300
+    env = make_env(m, n, k, games)
+    ref = orc.OracleEnv(m, n, k, games)
+    obs = env.reset()
+    ref.reset()
+    dones = torch.zeros(games, dtype=torch.bool, device=DEV)
+    wins = losses = draws = 0
+    p1_side = 0
+    rng = np.random.default_rng(3)
+    plies = 0
+    while not dones.all():
+        current_player = env.current_player                       # live mirror, as the reference reads it
+        active = ~dones
+        is_p1 = (current_player == p1_side) & active
+        moving = torch.nonzero(active).squeeze(1)
+        mask = obs["action_mask"]
+        # both "policies": a random legal cell (p1 flips the observation when white, as the reference does)
+        _ = torch.flip(obs["observation"][is_p1], dims=(1,)) if p1_side == 1 else obs["observation"][is_p1]
+        u = torch.from_numpy(rng.random(games)).to(DEV)
+        cnt = mask.sum(1)
+        j = (u * cnt).long().clamp(max=(cnt - 1).clamp(min=0))
+        actions = torch.argmax((mask & ((torch.cumsum(mask.long(), 1) - 1) == j[:, None])).long(), dim=1)
+        obs, rewards, step_dones = env.step_subset(actions[moving], moving)
+        o2, r2, d2 = ref.step_subset(actions[moving].cpu().numpy(), moving.cpu().numpy())
+        assert np.array_equal(rewards.cpu().numpy(), r2) and np.array_equal(step_dones.cpu().numpy(), d2)
+        assert np.array_equal(obs["observation"].cpu().numpy(), o2["observation"])
+        just = step_dones & ~dones
+        winners = (rewards == 1.0) & just
+        wins += int((winners & is_p1).sum())
+        losses += int((winners & ~is_p1).sum())
+        draws += int(((rewards == 0.0) & just).sum())
+        dones |= just
+        plies += 1
+        assert plies <= m * n
+    assert wins + losses + draws == games and wins > 0 and losses > 0
+    assert np.array_equal(env.current_player.cpu().numpy(), ref.current_player)
