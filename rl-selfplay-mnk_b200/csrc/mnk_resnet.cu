@@ -30,7 +30,6 @@
 #include "mnk_dispatch.cuh"
 
 #include <cuda_bf16.h>
-#include <cstdlib>
 
 namespace rn {
 constexpr int kC = 32;                        // tower channels
@@ -48,6 +47,10 @@ constexpr int kMmaWarp = 8;                   // warps 0-7 epilogue (lane quarte
 constexpr int kThreads = 32 * (kMmaWarp + 1); // warp 8: MMA issue + TMA
 constexpr int kTmemCols = 32 * kBlocksM;      // 256
 constexpr int kMaxLayers = 1 + 2 * 8;
+#ifndef MNK_POLL_BACKOFF_NS
+#define MNK_POLL_BACKOFF_NS 96
+#endif
+constexpr unsigned kPollBackoffNs = MNK_POLL_BACKOFF_NS;
 
 struct Smem {
     alignas(128) unsigned char act[2][kActBytes];
@@ -78,7 +81,7 @@ MNK_DEV void mbar_expect_tx(void* bar, u32 bytes) {
 // bounded wait: returns false instead of hanging if the phase never completes
 MNK_DEV bool mbar_wait(void* bar, u32 parity) {
     const u32 addr = smem_u32(bar);
-    for (int spin = 0; spin < (1 << 20); ++spin) {
+    for (int spin = 0; spin < (1 << 18); ++spin) {
         u32 done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -88,6 +91,9 @@ MNK_DEV bool mbar_wait(void* bar, u32 parity) {
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return true;
+        // back off: a spinning try_wait is a shared-memory access per poll, and 8 polling warps took ~a quarter
+        // of the shared-memory pipe away from the tensor core's operand reads (ncu, profiles/README.md)
+        __nanosleep(kPollBackoffNs);
     }
     return false;
 }
@@ -142,7 +148,6 @@ struct Params {
     float* policy_feat;               // f32 [num_envs][2*cells]
     float* value_feat;                // f32 [num_envs][cells]
     int* error;                       // set to 1 on an mbarrier timeout
-    int debug_noshift;                // timing experiment only (MNK_TOWER_DEBUG_NOSHIFT=1): all taps read unshifted rows
 };
 
 MNK_DEV void tmem_ld16(u32 taddr, u32 (&v)[16]) {
@@ -157,7 +162,7 @@ MNK_DEV void tmem_ld16(u32 taddr, u32 (&v)[16]) {
 
 // bias (+ skip) + ReLU + bf16 store of NCH channels [ch0, ch0+NCH) of pixel row i; returns the fp32 values
 template <int NCH>
-MNK_DEV void epilogue_row(Smem& sm, const u32* acc, const float* bias, int out_buf, int i, int ch0, bool skip, bool valid,
+MNK_DEV void epilogue_row(Smem& sm, const u32* acc, const float (&bias)[NCH], int out_buf, int i, int ch0, bool skip, bool valid,
                           bool store, float (&v)[NCH]) {
     constexpr int NKC = NCH / 8;
     uint4* out_row[NKC];
@@ -165,7 +170,7 @@ MNK_DEV void epilogue_row(Smem& sm, const u32* acc, const float* bias, int out_b
     for (int kc = 0; kc < NKC; ++kc)
         out_row[kc] = reinterpret_cast<uint4*>(&sm.act[out_buf][0]) + (size_t)(ch0 / 8 + kc) * kBufRows + (kMargin + i);
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) v[ch] = __uint_as_float(acc[ch]) + bias[ch0 + ch];
+    for (int ch = 0; ch < NCH; ++ch) v[ch] = __uint_as_float(acc[ch]) + bias[ch];
     if (skip) {
 #pragma unroll
         for (int kc = 0; kc < NKC; ++kc) {
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 2) resnet_tower_kernel(Params p) {
             for (int g = 0; g < kGroups; ++g) {
                 u32 acc = 0;
                 for (int tap = 0; tap < kTaps; ++tap) {
-                    const int off = p.debug_noshift ? 0 : (tap / 3 - 1) * p.pw + (tap % 3 - 1);
+                    const int off = (tap / 3 - 1) * p.pw + (tap % 3 - 1);
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const u64 b_desc = umma_desc(w_base + (u32)((tap * kChunks + 2 * ks) * kC) * 16, kC * 16, 128);
                         const u32 a_addr0 = a_base + (u32)(2 * ks) * (kBufRows * 16) + (u32)(kMargin + 128 * g * kGroupBlocks + off) * 16;
@@ -299,7 +304,12 @@ __global__ void __launch_bounds__(kThreads, 2) resnet_tower_kernel(Params p) {
                 __syncwarp();
             }
         } else {
-            const float* bias = sm.bias[L];
+            float bias[16];   // this warp's 16 channels of the layer's folded bias: 4 vector loads per layer, not 16 scalar loads per block
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 b4 = reinterpret_cast<const float4*>(&sm.bias[L][16 * half])[q4];
+                bias[4 * q4] = b4.x; bias[4 * q4 + 1] = b4.y; bias[4 * q4 + 2] = b4.z; bias[4 * q4 + 3] = b4.w;
+            }
             for (int j = 0; j < kBlocksM; ++j) {
                 if (j % kGroupBlocks == 0) {
                     ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[j / kGroupBlocks], L & 1)) != 0;   // warp-uniform
@@ -374,7 +384,6 @@ extern "C" int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, cons
     p.bits = reinterpret_cast<const u64*>(st->bits);
     p.swap = swap; p.weights = static_cast<const unsigned char*>(weights); p.bias = bias;
     p.head_w = head_w; p.head_b = head_b; p.policy_feat = policy_feat; p.value_feat = value_feat; p.error = error;
-    p.debug_noshift = getenv("MNK_TOWER_DEBUG_NOSHIFT") != nullptr;
     const size_t smem = sizeof(rn::Smem) + 128;
     static bool configured = false;
     if (!configured) {
