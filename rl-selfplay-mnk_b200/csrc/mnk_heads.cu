@@ -6,16 +6,16 @@
 //     policy: LayerNorm(2A) -> ReLU -> Linear(2A,128) -> LayerNorm(128) -> ReLU -> Linear(128,A)   = logits
 //     value : LayerNorm(A)  -> ReLU -> Linear(A,128)  -> LayerNorm(128) -> ReLU -> Linear(128,1) -> Tanh
 // 2% of the forward's FLOPs, but 14 small library kernels per forward when run through torch modules
-// (they cost as much wall time as the whole tower at 32k envs).  Here a CTA of 256 threads takes 8
-// samples at a time: warp w normalises sample w (shuffle reductions), the two hidden layers are
-// computed with one thread per (hidden unit, 4 samples) reading the transposed fp32 weight matrices
+// (they cost as much wall time as the whole tower at 32k envs).  Here a CTA of 256 threads takes 16
+// samples at a time: warp w normalises samples w and w+8 (shuffle reductions), the two hidden layers are
+// computed with one thread per (hidden unit, 8 samples) reading the transposed fp32 weight matrices
 // through the read-only path (coalesced over units, L1/L2 resident: 166 KB at 9x9) and the
-// activations as float4 broadcasts from shared memory.  fp32 throughout (matches torch to ~1e-6).
+// activations as float4 broadcasts from shared memory (k-major, 16 samples per k).  fp32 throughout (matches torch to ~1e-6).
 #include "mnk_dispatch.cuh"
 
 namespace hd {
 constexpr int kH = 128;          // head_hidden_dim of resnet_b_s
-constexpr int kSB = 8;           // samples per CTA iteration (= warps)
+constexpr int kSB = 16;          // samples per CTA iteration (2 per warp; 8 per thread in the dense layers)
 constexpr int kThreads = 256;
 constexpr float kEps = 1e-5f;    // torch.nn.LayerNorm default
 
@@ -26,8 +26,47 @@ MNK_DEV float warp_sum(float v) {
 }
 
 // LayerNorm + ReLU of `len` values of sample s held at x[k*kSB + s] (k-major so that the next layer can
-// fetch 4 samples of one k with a single float4), in place; one warp per sample
-MNK_DEV void layernorm_relu(float* x, int s, int len, const float* __restrict__ gamma, const float* __restrict__ beta, int lane) {
+// fetch 8 samples of one k with two float4), in place; one warp per sample.  The values are pulled into
+// registers once (the k-major layout makes lane-strided shared-memory passes 16-way bank conflicted).
+constexpr int kMaxItems = 24;    // per lane: covers len <= 768 (19x19: 2A = 722)
+
+MNK_DEV void layernorm_relu_regs(float (&v)[kMaxItems], int len, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float* x, int s, int lane) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxItems; ++i) sum += (lane + 32 * i < len) ? v[i] : 0.f;
+    const float mean = warp_sum(sum) / (float)len;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxItems; ++i) {
+        const float d = (lane + 32 * i < len) ? v[i] - mean : 0.f;
+        sq += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)len + kEps);
+#pragma unroll
+    for (int i = 0; i < kMaxItems; ++i) {
+        const int k = lane + 32 * i;
+        if (k < len) x[k * kSB + s] = fmaxf((v[i] - mean) * rstd * __ldg(gamma + k) + __ldg(beta + k), 0.f);
+    }
+}
+
+// source = global row (coalesced) or the k-major shared-memory column of sample s
+MNK_DEV void layernorm_relu(const float* __restrict__ grow, bool live, float* x, int s, int len,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, int lane) {
+    if (len <= 32 * kMaxItems) {
+        float v[kMaxItems];
+#pragma unroll
+        for (int i = 0; i < kMaxItems; ++i) {
+            const int k = lane + 32 * i;
+            v[i] = (k < len) ? (grow ? (live ? __ldg(grow + k) : 0.f) : x[k * kSB + s]) : 0.f;
+        }
+        layernorm_relu_regs(v, len, gamma, beta, x, s, lane);
+        return;
+    }
+    // very large boards: shared-memory passes
+    if (grow)
+        for (int k = lane; k < len; k += 32) x[k * kSB + s] = live ? __ldg(grow + k) : 0.f;
+    __syncwarp();
     float sum = 0.f;
     for (int k = lane; k < len; k += 32) sum += x[k * kSB + s];
     const float mean = warp_sum(sum) / (float)len;
@@ -37,26 +76,29 @@ MNK_DEV void layernorm_relu(float* x, int s, int len, const float* __restrict__ 
         sq += d * d;
     }
     const float rstd = rsqrtf(warp_sum(sq) / (float)len + kEps);
-    for (int k = lane; k < len; k += 32) {
-        const float y = (x[k * kSB + s] - mean) * rstd * __ldg(gamma + k) + __ldg(beta + k);
-        x[k * kSB + s] = fmaxf(y, 0.f);
-    }
+    for (int k = lane; k < len; k += 32)
+        x[k * kSB + s] = fmaxf((x[k * kSB + s] - mean) * rstd * __ldg(gamma + k) + __ldg(beta + k), 0.f);
 }
 
-// out[j][4 samples] = bias[j] + sum_k wT[k][j] * x[k][samples]   for j = unit, samples = 4*half .. 4*half+3
-MNK_DEV void dense4(const float* __restrict__ wT, int ld, const float* __restrict__ bias, const float* x, int len, int unit,
-                    int half, float (&acc)[4]) {
+// out[j][8 samples] = bias[j] + sum_k wT[k][j] * x[k][samples]   for j = unit, samples = 8*half .. 8*half+7
+MNK_DEV void dense8(const float* __restrict__ wT, int ld, const float* __restrict__ bias, const float* x, int len, int unit,
+                    int half, float (&acc)[8]) {
     const float b = __ldg(bias + unit);
-    acc[0] = acc[1] = acc[2] = acc[3] = b;
-    const float4* xv = reinterpret_cast<const float4*>(x) + half;      // x[k*8 + 4*half ..]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = b;
+    const float4* xv = reinterpret_cast<const float4*>(x) + 2 * half;      // x[k*16 + 8*half ..]
 #pragma unroll 4
     for (int k = 0; k < len; ++k) {
         const float w = __ldg(wT + (size_t)k * ld + unit);
-        const float4 v = xv[2 * k];
-        acc[0] = fmaf(w, v.x, acc[0]);
-        acc[1] = fmaf(w, v.y, acc[1]);
-        acc[2] = fmaf(w, v.z, acc[2]);
-        acc[3] = fmaf(w, v.w, acc[3]);
+        const float4 v0 = xv[4 * k], v1 = xv[4 * k + 1];
+        acc[0] = fmaf(w, v0.x, acc[0]);
+        acc[1] = fmaf(w, v0.y, acc[1]);
+        acc[2] = fmaf(w, v0.z, acc[2]);
+        acc[3] = fmaf(w, v0.w, acc[3]);
+        acc[4] = fmaf(w, v1.x, acc[4]);
+        acc[5] = fmaf(w, v1.y, acc[5]);
+        acc[6] = fmaf(w, v1.z, acc[6]);
+        acc[7] = fmaf(w, v1.w, acc[7]);
     }
 }
 
@@ -74,44 +116,53 @@ heads_kernel(const float* __restrict__ pf, const float* __restrict__ vf, long lo
 
     for (long long r0 = (long long)blockIdx.x * kSB; r0 < rows; r0 += (long long)gridDim.x * kSB) {
         // 1. load (coalesced per sample row) + LayerNorm + ReLU; rows past the end are zero-filled
-        {
-            const long long r = r0 + warp;
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+            const int sidx = warp + 8 * rep;
+            const long long r = r0 + sidx;
             const bool live = r < rows;
-            for (int k = lane; k < two; k += 32) xp[k * kSB + warp] = live ? __ldg(pf + (size_t)r * two + k) : 0.f;
-            for (int k = lane; k < cells; k += 32) xv[k * kSB + warp] = live ? __ldg(vf + (size_t)r * cells + k) : 0.f;
-            __syncwarp();
-            layernorm_relu(xp, warp, two, w.p_ln1_w, w.p_ln1_b, lane);
-            layernorm_relu(xv, warp, cells, w.v_ln1_w, w.v_ln1_b, lane);
+            const long long rr = live ? r : 0;
+            layernorm_relu(pf + (size_t)rr * two, live, xp, sidx, two, w.p_ln1_w, w.p_ln1_b, lane);
+            layernorm_relu(vf + (size_t)rr * cells, live, xv, sidx, cells, w.v_ln1_w, w.v_ln1_b, lane);
         }
         __syncthreads();
-        // 2. first Linear of both heads: thread = (hidden unit, 4 samples)
+        // 2. first Linear of both heads: thread = (hidden unit, 8 samples)
         {
-            float acc[4];
-            dense4(w.p_w1t, kH, w.p_b1, xp, two, unit, half, acc);
-            *reinterpret_cast<float4*>(hp + unit * kSB + 4 * half) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            dense4(w.v_w1t, kH, w.v_b1, xv, cells, unit, half, acc);
-            *reinterpret_cast<float4*>(hv + unit * kSB + 4 * half) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            float acc[8];
+            dense8(w.p_w1t, kH, w.p_b1, xp, two, unit, half, acc);
+            float4* dst = reinterpret_cast<float4*>(hp + unit * kSB + 8 * half);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            dense8(w.v_w1t, kH, w.v_b1, xv, cells, unit, half, acc);
+            dst = reinterpret_cast<float4*>(hv + unit * kSB + 8 * half);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
         __syncthreads();
         // 3. LayerNorm(128) + ReLU per sample
-        layernorm_relu(hp, warp, kH, w.p_ln2_w, w.p_ln2_b, lane);
-        layernorm_relu(hv, warp, kH, w.v_ln2_w, w.v_ln2_b, lane);
-        __syncthreads();
-        // 4. output layers: logits (thread = (cell, 4 samples)), value (warp = sample)
-        for (int a = unit; a < cells; a += kH) {
-            float acc[4];
-            dense4(w.p_w2t, cells, w.p_b2, hp, kH, a, half, acc);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long long r = r0 + 4 * half + i;
+        for (int rep = 0; rep < 2; ++rep) {
+            layernorm_relu(nullptr, true, hp, warp + 8 * rep, kH, w.p_ln2_w, w.p_ln2_b, lane);
+            layernorm_relu(nullptr, true, hv, warp + 8 * rep, kH, w.v_ln2_w, w.v_ln2_b, lane);
+        }
+        __syncthreads();
+        // 4. output layers: logits (thread = (cell, 8 samples)), value (warp = 2 samples)
+        for (int a = unit; a < cells; a += kH) {
+            float acc[8];
+            dense8(w.p_w2t, cells, w.p_b2, hp, kH, a, half, acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long r = r0 + 8 * half + i;
                 if (r < rows) logits[(size_t)r * cells + a] = acc[i];
             }
         }
-        {
+#pragma unroll
+        for (int rep = 0; rep < 2; ++rep) {
+            const int sidx = warp + 8 * rep;
             float dot = 0.f;
-            for (int k = lane; k < kH; k += 32) dot = fmaf(hv[k * kSB + warp], __ldg(w.v_w2 + k), dot);
+            for (int k = lane; k < kH; k += 32) dot = fmaf(hv[k * kSB + sidx], __ldg(w.v_w2 + k), dot);
             dot = warp_sum(dot);
-            const long long r = r0 + warp;
+            const long long r = r0 + sidx;
             if (lane == 0 && r < rows) values[r] = tanhf(dot + __ldg(w.v_b2));
         }
         __syncthreads();   // smem is rewritten by the next batch

@@ -31,6 +31,15 @@ for ne in (4096, 32768, 262144):
         lg, v = native.forward_env(env)
     e1.record(); torch.cuda.synchronize()
     ms_full = e0.elapsed_time(e1) / reps
+    pf, vf = native.features(env._st, ne, m * n, None)
+    for _ in range(3):
+        native.tails(pf, vf)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        native.tails(pf, vf)
+    e1.record(); torch.cuda.synchronize()
+    ms_heads = e0.elapsed_time(e1) / reps
     native.torch_heads = True
     e0.record()
     for _ in range(reps):
@@ -40,5 +49,5 @@ for ne in (4096, 32768, 262144):
     native.torch_heads = False
     tf = ne * flops_per_sample * 0.98 / (ms * 1e-3) / 1e12
     print(f"{m}x{n} envs={ne}: tower {ms:.3f} ms = {ne/ms*1e3/1e6:.2f} M samples/s = {tf:.1f} useful TFLOP/s "
-          f"({tf/peaks['bf16_tflops_sustained']:.3f} of sustained bf16 peak); tower+fused heads {ms_full:.3f} ms (tower+torch heads {ms_torch:.3f} ms)")
+          f"({tf/peaks['bf16_tflops_sustained']:.3f} of sustained bf16 peak); heads kernel {ms_heads:.3f} ms; forward_env {ms_full:.3f} ms (with torch heads {ms_torch:.3f} ms)")
 native.check_error()
