@@ -245,14 +245,19 @@ def run_b200_arm(args):
     snap_bits, snap_meta = env._bits.clone(), env._meta.clone()
 
     # ---- pre-generate the action trace by playing the games once (untimed) --------------------------
-    actions = torch.empty((total, envs), dtype=torch.long, device=dev)
+    # the CPU baseline replays the head of the same trace: generate enough batches for it even when K is small
+    want_cpu = world == 1 and not args.no_cpu_baseline
+    gen = max(total, W + args.cpu_steps) if want_cpu else total
+    actions = torch.empty((gen, envs), dtype=torch.long, device=dev)
     stats = torch.zeros(3, dtype=torch.float64, device=dev)     # episodes, wins, plies
-    for t in range(total):
+    want_digest = None
+    for t in range(gen):
         env.random_legal_actions(seed, MIX_PLIES + t, out=actions[t])
         _, r, d = env.step_autoreset(actions[t], materialise=False)
-        if t >= W:
+        if W <= t < total:
             stats += torch.stack([d.sum(), r.sum(), torch.tensor(float(envs), device=dev)]).double()
-    want_digest = env.state_checksum()
+        if t == total - 1:
+            want_digest = env.state_checksum()              # state after exactly W + K steps
 
     def restore():
         env._bits.copy_(snap_bits)
