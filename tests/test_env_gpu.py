@@ -266,3 +266,32 @@ def test_tournament_style_consumer_on_raw_env():
         assert plies <= m * n
     assert wins + losses + draws == games and wins > 0 and losses > 0
     assert np.array_equal(env.current_player.cpu().numpy(), ref.current_player)
+
+
+def test_strict_counters_of_the_c_abi():
+    """mnk_step's `illegal` output (include/mnk_b200.h): [0] counts moves onto occupied / out-of-range cells,
+    [1] encodes the smallest offending env; the moves are still applied, as in the reference."""
+    import ctypes
+    from mnk_b200 import _lib
+    env = make_env(9, 9, 5, 200)
+    env.reset()
+    a = torch.zeros(200, dtype=torch.long, device=DEV)
+    env.step(a)                                            # cell 0 now occupied everywhere
+    a = torch.full((200,), 5, dtype=torch.long, device=DEV)
+    a[17] = 0                                              # occupied
+    a[150] = 0
+    a[60] = 81                                             # out of range
+    illegal = torch.zeros(2, dtype=torch.int32, device=DEV)
+    rewards = torch.empty(200, device=DEV)
+    dones = torch.empty(200, dtype=torch.bool, device=DEV)
+    rc = _lib.lib().mnk_step(env._stp, a.data_ptr(), None, 200, rewards.data_ptr(), dones.data_ptr(), None, None,
+                             illegal.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    cnt, enc = illegal.tolist()
+    assert cnt == 3 and 0x7FFFFFFF - enc == 17
+    assert env.move_counts.eq(2).all()                     # every move counted, illegal ones included
+    idx = torch.tensor([3, 60], device=DEV)
+    illegal.zero_()
+    rc = _lib.lib().mnk_step(env._stp, torch.tensor([5, 1], device=DEV).data_ptr(), idx.data_ptr(), 2, rewards.data_ptr(),
+                             dones.data_ptr(), None, None, illegal.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    assert rc == 0 and illegal.tolist()[0] == 1 and 0x7FFFFFFF - illegal.tolist()[1] == 3
