@@ -74,10 +74,20 @@ class MaskedCategorical:
     def mode(self) -> torch.Tensor:
         return masked_sample(self._raw, self._mask, deterministic=True, want_log_prob=False)[0]
 
+    def _needs_autograd(self) -> bool:
+        return self._raw.requires_grad and torch.is_grad_enabled()
+
     def log_prob(self, actions: torch.Tensor) -> torch.Tensor:
+        if self._needs_autograd() or not self._raw.is_cuda:     # learner side: differentiable torch ops
+            return self.logits.gather(1, actions.long().unsqueeze(1)).squeeze(1)
         return masked_sample(self._raw, self._mask, given=actions)[1]
 
     def entropy(self) -> torch.Tensor:
+        if self._needs_autograd() or not self._raw.is_cuda:
+            lg = self.logits
+            finite = torch.isfinite(lg)
+            lg0 = torch.where(finite, lg, torch.zeros_like(lg))      # keeps -inf out of the product AND of its gradient
+            return -(lg0.exp() * finite * lg0).sum(dim=1)
         given = torch.zeros(self._raw.shape[0], dtype=torch.long, device=self._raw.device)
         return masked_sample(self._raw, self._mask, given=given, want_log_prob=False, want_entropy=True)[2]
 

@@ -45,7 +45,15 @@ def _worker(rank, world, port, out):
     mdist.reduce_stats(stats)
     t_ms = torch.tensor([10.0 + rank], dtype=torch.float64)
     mdist.reduce_stats(t_ms, op=dist.ReduceOp.MAX)          # bench.py takes the max time over ranks
-    out[rank] = (stats.tolist(), t_ms.item())
+    # learner collectives: gradient averaging and global advantage moments
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(4, 3)
+    lin.weight.grad = torch.full_like(lin.weight, float(rank + 1))
+    lin.bias.grad = torch.arange(3, dtype=torch.float32) * (rank + 1)
+    mdist.average_gradients(lin.parameters(), w)
+    shard_vals = torch.arange(offset, offset + count, dtype=torch.float32) * 0.01
+    mean, std = mdist.global_mean_std(shard_vals)
+    out[rank] = (stats.tolist(), t_ms.item(), lin.weight.grad[0, 0].item(), lin.bias.grad.tolist(), mean.item(), std.item())
     dist.destroy_process_group()
 
 
@@ -58,5 +66,8 @@ def test_two_rank_gloo_stats_allreduce():
         ids = np.arange(1001, dtype=np.float64)
         want = [1001.0, ids.sum(), 2 * ids.sum(), (ids % 3 == 0).sum(), (ids % 3 == 1).sum(), (ids % 3 == 2).sum()]
         for rank in range(world):
-            stats, tmax = out[rank]
+            stats, tmax, gw, gb, mean, std = out[rank]
             assert stats == want and tmax == 11.0
+            assert gw == 1.5 and gb == [0.0, 1.5, 3.0]                      # mean of the two ranks' gradients
+            full = np.arange(1001, dtype=np.float64) * 0.01
+            assert abs(mean - full.mean()) < 1e-5 and abs(std - full.std(ddof=1)) < 1e-5
