@@ -21,7 +21,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from typing import Callable, Dict, Optional, Tuple
+from typing import Callable, Dict, Optional
 
 import numpy as np
 

@@ -9,7 +9,6 @@ sample / log_prob / entropy run on the warp-per-row sampler.
 """
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
