@@ -461,14 +461,18 @@ def run_rollout_arm(args):
     col._last_obs = {"observation": None, "action_mask": None}
     warm_buf = RolloutBuffer(max(W, MIX_PLIES // 2), envs, (2, M, N_COLS), CELLS, device=dev, k=K_LINE)
     col.collect(agent, wr, warm_buf)                       # warm-up: also brings games to a stationary depth mix
+    use_graph = not args.no_graph
     buf = RolloutBuffer(K, envs, (2, M, N_COLS), CELLS, device=dev, k=K_LINE)
+    if use_graph:                                          # capture the K-step rollout once; its first replay is untimed
+        col.collect(agent, wr, buf, graph=True)
+        buf.reset()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
     ev0.record()
-    stats = col.collect(agent, wr, buf)                    # K steps; ends with the NCCL all-reduce + one host read
+    stats = col.collect(agent, wr, buf, graph=use_graph)   # K steps; ends with the NCCL all-reduce + one host read
     ev1.record()
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t0)
@@ -496,7 +500,8 @@ def run_rollout_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"cfg3: gomoku 9x9x5 self-play rollout, {envs} envs/GPU x {K} steps, resnet_b_s agent + frozen "
                                    "copy as opponent (random-init weights), tcgen05 forward from bitboards, Gumbel-max sampling, "
-                                   "fused wrapper, packed PPO buffer, on-device episode stats",
+                                   "fused wrapper, packed PPO buffer, on-device episode stats"
+                                   + (", the whole K-step rollout replayed as one CUDA graph" if use_graph else ", eager launches"),
                        "envs_per_gpu": envs, "global_envs": envs * world,
                        "l2": f"per step the towers stream {envs * 72 / 2**20:.1f} MiB of bitboards and {envs * 972 * 2 / 2**20:.0f} MiB of "
                              "head features; rollout buffer slots are distinct per step",
@@ -529,6 +534,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=60)
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="cfg3: eager launches instead of one CUDA graph per rollout")
     ap.add_argument("--no-pdl", action="store_true", help="plain launches instead of programmatic dependent launch")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

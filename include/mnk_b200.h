@@ -137,14 +137,16 @@ int mnk_random_legal(const mnk_state_t* st, uint64_t seed, uint64_t counter, int
  * log_prob(a) = logit_a - logsumexp, entropy = -sum p log p.  One warp per row.
  *   logits       f32[rows][row_stride] (row_stride >= num_actions, in elements), num_actions <= 512
  *   mask         u8[rows][num_actions] or NULL (everything legal)
+ *   counter_base NULL, or a device u64 added to `counter` (a captured CUDA graph bakes `counter`; bumping the
+ *                device value between replays gives fresh draws)
  *   given        NULL => draw the action (Gumbel-max on Philox(seed; row_offset + row, counter)),
  *                deterministic != 0 => argmax, first index on ties (policy.py:49-50);
  *                else i64[rows]: evaluate these actions instead of sampling
  *   actions      i64[rows] out (may be NULL when `given` is set)
  *   log_probs    f32[rows] or NULL, entropy f32[rows] or NULL */
 int mnk_masked_sample(const float* logits, int64_t row_stride, const uint8_t* mask, int32_t num_actions,
-                      int64_t rows, uint64_t seed, uint64_t counter, int64_t row_offset, int deterministic,
-                      const int64_t* given, int64_t* actions, float* log_probs, float* entropy, void* stream);
+                      int64_t rows, uint64_t seed, uint64_t counter, const uint64_t* counter_base, int64_t row_offset,
+                      int deterministic, const int64_t* given, int64_t* actions, float* log_probs, float* entropy, void* stream);
 
 /* ---- self-play wrapper: src/selfplay/torch_self_play_wrapper.py ------------------------------ */
 
@@ -154,6 +156,8 @@ typedef struct mnk_selfplay {
     uint32_t* episodes;   /* u32[num_envs] episodes started per env: the Philox counter of the side draw   */
     uint64_t seed;        /* key of the side / opponent draws                                             */
     int64_t env_offset;   /* global id of local env 0 (draws do not depend on the sharding)               */
+    const uint64_t* counter_base; /* NULL, or a device u64 added to step_counter of the fused random       */
+                          /* opponent (lets a captured CUDA graph draw fresh numbers on every replay)     */
 } mnk_selfplay_t;
 
 #define MNK_SP_ACTIONS_I32 1u        /* agent / opponent actions are int32_t[]                              */

@@ -252,8 +252,11 @@ def philox4x32(c0, c1, c2, c3, k0: int, k1: int, rounds: int = 10):
 def _draw_u32(seed: int, global_env_ids: np.ndarray, counter, stream: int) -> np.ndarray:
     gid = np.asarray(global_env_ids, dtype=np.uint64)
     ctr = np.asarray(counter, dtype=np.uint64)
+    # 64-bit counter: low word = Philox counter word, high word folded into the key (csrc/mnk_device.cuh::mnk_philox)
+    hi = int(ctr.max() >> np.uint64(32)) if ctr.size else 0
+    assert ctr.ndim == 0 or hi == 0, "per-row counters must fit 32 bits"
     out = philox4x32(gid & np.uint64(0xFFFFFFFF), gid >> np.uint64(32), ctr & np.uint64(0xFFFFFFFF),
-                     np.uint64(stream), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+                     np.uint64(stream), seed & 0xFFFFFFFF, ((seed >> 32) ^ hi) & 0xFFFFFFFF)
     return out[0]
 
 

@@ -535,9 +535,11 @@ MNK_DEV uint4 philox4x32_10(uint4 c, u32 k0, u32 k1) {
     return c;
 }
 
-MNK_DEV uint4 mnk_philox(u64 seed, u64 global_env, u32 counter, u32 stream) {
-    return philox4x32_10(make_uint4((u32)global_env, (u32)(global_env >> 32), counter, stream), (u32)seed,
-                         (u32)(seed >> 32));
+// counter is 64-bit: its low word is a Philox counter word, its high word is folded into the key, so a
+// device-resident base (CUDA-graph replays, see mnk_masked_sample) can advance it without ever repeating
+MNK_DEV uint4 mnk_philox(u64 seed, u64 global_env, u64 counter, u32 stream) {
+    return philox4x32_10(make_uint4((u32)global_env, (u32)(global_env >> 32), (u32)counter, stream), (u32)seed,
+                         (u32)(seed >> 32) ^ (u32)(counter >> 32));
 }
 
 // uniformly random empty cell from the bitboards (RandomPolicy.act, policy.py:17-29)

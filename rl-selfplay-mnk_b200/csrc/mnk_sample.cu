@@ -13,12 +13,14 @@
 template <int ITEMS>
 __global__ void __launch_bounds__(128)
 masked_sample_kernel(const float* __restrict__ logits, long long row_stride, const u8* __restrict__ mask, int num_actions,
-                     long long rows, u64 seed, u32 counter, long long row_offset, int deterministic,
+                     long long rows, u64 seed, u64 counter, const u64* __restrict__ counter_base, long long row_offset,
+                     int deterministic,
                      const int64_t* __restrict__ given, int64_t* __restrict__ actions, float* __restrict__ log_probs,
                      float* __restrict__ entropy) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
+    if (counter_base != nullptr) counter += *counter_base;   // device-resident base: lets a captured graph draw fresh numbers per replay
     const float* lrow = logits + (size_t)row * row_stride;
     const u8* mrow = mask ? mask + (size_t)row * num_actions : nullptr;
 
@@ -94,7 +96,8 @@ masked_sample_kernel(const float* __restrict__ logits, long long row_stride, con
 }
 
 extern "C" int mnk_masked_sample(const float* logits, int64_t row_stride, const uint8_t* mask, int32_t num_actions,
-                                 int64_t rows, uint64_t seed, uint64_t counter, int64_t row_offset, int deterministic,
+                                 int64_t rows, uint64_t seed, uint64_t counter, const uint64_t* counter_base,
+                                 int64_t row_offset, int deterministic,
                                  const int64_t* given, int64_t* actions, float* log_probs, float* entropy,
                                  void* stream) {
     if (logits == nullptr || (given == nullptr && actions == nullptr)) return MNK_ERR_NULL;
@@ -104,8 +107,9 @@ extern "C" int mnk_masked_sample(const float* logits, int64_t row_stride, const 
     const unsigned blocks = (unsigned)((rows + 3) / 4);
     const int items = (num_actions + 31) / 32;
 #define MNK_LAUNCH_SAMPLE(I)                                                                                          \
-    masked_sample_kernel<I><<<blocks, 128, 0, s>>>(logits, row_stride, mask, num_actions, rows, seed, (u32)counter,  \
-                                                   row_offset, deterministic, given, actions, log_probs, entropy)
+    masked_sample_kernel<I><<<blocks, 128, 0, s>>>(logits, row_stride, mask, num_actions, rows, seed, (u64)counter,  \
+                                                   reinterpret_cast<const u64*>(counter_base), row_offset, deterministic, given,  \
+                                                   actions, log_probs, entropy)
     if (items <= 1) MNK_LAUNCH_SAMPLE(1);
     else if (items <= 3) MNK_LAUNCH_SAMPLE(3);
     else if (items <= 6) MNK_LAUNCH_SAMPLE(6);

@@ -110,7 +110,7 @@ template <class G, bool ACT32, bool FUSED_RANDOM>
 __global__ void __launch_bounds__(tile_cta_threads<G>())
 selfplay_finish_kernel(G g, mnk_state_t st, mnk_selfplay_t sp, const void* __restrict__ agent_actions,
                        const int64_t* __restrict__ forced_sides, const void* __restrict__ opp_actions,
-                       const u8* __restrict__ opp_active, u32 step_counter, float* __restrict__ rewards,
+                       const u8* __restrict__ opp_active, u64 step_counter, float* __restrict__ rewards,
                        u8* __restrict__ terminated, float* __restrict__ obs, u8* __restrict__ mask, u32 flags) {
     __shared__ u32 tile_smem[TileStream<G>::kWords];
     const int lane = threadIdx.x & 31;
@@ -141,7 +141,8 @@ selfplay_finish_kernel(G g, mnk_state_t st, mnk_selfplay_t sp, const void* __res
                 opp = out.opp;
                 if (opp != OPP_IDLE) {
                     const bool det = (flags & MNK_SP_DETERMINISTIC_OPP) != 0;
-                    const u32 rnd = det ? 0u : mnk_philox(sp.seed, (u64)(sp.env_offset + e), step_counter, MNK_STREAM_OPPONENT).x;
+                    const u64 ctr = step_counter + (sp.counter_base ? *sp.counter_base : 0ull);
+                    const u32 rnd = det ? 0u : mnk_philox(sp.seed, (u64)(sp.env_offset + e), ctr, MNK_STREAM_OPPONENT).x;
                     oa = pick_legal(g, s, rnd, det);
                 }
             } else {
@@ -212,10 +213,10 @@ int mnk_selfplay_opponent(const mnk_state_t* st, const mnk_selfplay_t* sp, const
         const int threads = (obs != nullptr || mask != nullptr) ? tile_cta_threads<G>() : 32;
         if (flags & MNK_SP_ACTIONS_I32)
             selfplay_finish_kernel<G, true, false><<<blocks, threads, 0, s>>>(g, *st, *sp, nullptr, nullptr, opp_actions, opp_active,
-                                                                              0u, rewards, terminated, obs, mask, flags);
+                                                                              0ull, rewards, terminated, obs, mask, flags);
         else
             selfplay_finish_kernel<G, false, false><<<blocks, threads, 0, s>>>(g, *st, *sp, nullptr, nullptr, opp_actions, opp_active,
-                                                                               0u, rewards, terminated, obs, mask, flags);
+                                                                               0ull, rewards, terminated, obs, mask, flags);
         return mnk_launch_status();
     });
 }
@@ -235,10 +236,10 @@ int mnk_selfplay_step_random(const mnk_state_t* st, const mnk_selfplay_t* sp, co
         const int threads = (obs != nullptr || mask != nullptr) ? tile_cta_threads<G>() : 32;
         if (flags & MNK_SP_ACTIONS_I32)
             selfplay_finish_kernel<G, true, true><<<blocks, threads, 0, s>>>(g, *st, *sp, actions, forced_sides, nullptr, nullptr,
-                                                                             (u32)step_counter, rewards, terminated, obs, mask, flags);
+                                                                             (u64)step_counter, rewards, terminated, obs, mask, flags);
         else
             selfplay_finish_kernel<G, false, true><<<blocks, threads, 0, s>>>(g, *st, *sp, actions, forced_sides, nullptr, nullptr,
-                                                                              (u32)step_counter, rewards, terminated, obs, mask, flags);
+                                                                              (u64)step_counter, rewards, terminated, obs, mask, flags);
         return mnk_launch_status();
     });
 }

@@ -35,7 +35,7 @@ class MnkState(ctypes.Structure):
 class MnkSelfplay(ctypes.Structure):
     """struct mnk_selfplay of include/mnk_b200.h."""
     _fields_ = [("agent_side", ctypes.c_void_p), ("pending", ctypes.c_void_p), ("episodes", ctypes.c_void_p),
-                ("seed", ctypes.c_uint64), ("env_offset", ctypes.c_int64)]
+                ("seed", ctypes.c_uint64), ("env_offset", ctypes.c_int64), ("counter_base", ctypes.c_void_p)]
 
 
 class MnkHeadsWeights(ctypes.Structure):
@@ -105,7 +105,7 @@ SIGNATURES = {
     "mnk_export_meta": (_I32, [_ST, _VP, _VP, _VP]),
     "mnk_import_meta": (_I32, [_ST, _VP, _VP, _VP]),
     "mnk_random_legal": (_I32, [_ST, _U64, _U64, _I64, _I32, _VP, _VP]),
-    "mnk_masked_sample": (_I32, [_VP, _I64, _VP, _I32, _I64, _U64, _U64, _I64, _I32, _VP, _VP, _VP, _VP, _VP]),
+    "mnk_masked_sample": (_I32, [_VP, _I64, _VP, _I32, _I64, _U64, _U64, _VP, _I64, _I32, _VP, _VP, _VP, _VP, _VP]),
     "mnk_selfplay_agent": (_I32, [_ST, _SP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
     "mnk_selfplay_opponent": (_I32, [_ST, _SP, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
     "mnk_selfplay_step_random": (_I32, [_ST, _SP, _VP, _VP, _U64, _VP, _VP, _VP, _VP, _U32, _VP]),

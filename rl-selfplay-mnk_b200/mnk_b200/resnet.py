@@ -154,6 +154,7 @@ class NativeNNPolicy(Policy):
         self.net = NativeResNet(model, device=device)
         self.seed = seed
         self._calls = 0
+        self.counter_base: Optional[torch.Tensor] = None     # see TorchSelfPlayWrapper.counter_base
 
     def act_from_env(self, env, counter: int, deterministic: bool = False) -> torch.Tensor:
         """Action for the side to move of every env, straight from the bitboards (the wrapper's dense
@@ -161,10 +162,10 @@ class NativeNNPolicy(Policy):
         swap = (env._meta & 1).to(torch.uint8)
         logits, _ = self.net.forward_env(env, swap)
         return masked_sample(logits, env.legal_mask(), seed=self.seed, counter=counter, row_offset=env.env_offset,
-                             deterministic=deterministic, want_log_prob=False)[0]
+                             deterministic=deterministic, want_log_prob=False, counter_base=self.counter_base)[0]
 
     def act(self, obs, deterministic: bool = False) -> torch.Tensor:
         dist, _ = self.net.forward(obs["observation"], obs["action_mask"])
         self._calls += 1
         return masked_sample(dist._raw, dist._mask, seed=self.seed, counter=self._calls, deterministic=deterministic,
-                             want_log_prob=False)[0]
+                             want_log_prob=False, counter_base=self.counter_base)[0]

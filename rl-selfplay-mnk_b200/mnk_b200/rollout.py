@@ -193,33 +193,78 @@ class RolloutCollector:
         self._ep_len = torch.zeros(num_envs, dtype=torch.float32, device=self._dev)
         self._calls = 0
 
-    def collect(self, network, vec_env, buffer: RolloutBuffer, n_steps: Optional[int] = None) -> RolloutStats:
+    def _stats_kernel(self, rewards, dones, totals):
+        with torch.cuda.device(self._dev):                 # ppo.py:110-120 without host reads
+            check(self._L.mnk_episode_stats(_ptr(rewards), _ptr(dones), self.num_envs, _ptr(self._ep_reward),
+                                             _ptr(self._ep_len), _ptr(totals),
+                                             torch.cuda.current_stream(self._dev).cuda_stream), "mnk_episode_stats")
+
+    def _native_step(self, network, vec_env, buffer, totals, counter_base=None):
+        """One agent step on the bitboard-fed path: tcgen05 forward, sampler, packed store, fused wrapper step."""
+        env = vec_env.env
+        with torch.no_grad():
+            logits, values = network.forward_env(env, swap=vec_env._side)
+            self._calls += 1
+            actions, log_probs, _ = masked_sample(logits, env.legal_mask(fix_all_masked=True), seed=self.seed,
+                                                  counter=self._calls, row_offset=self.row_offset, counter_base=counter_base)
+        buffer.store_obs_from(vec_env)
+        _, rewards, terminateds, truncateds, _ = vec_env.step(actions, materialise=False)
+        dones = terminateds | truncateds
+        buffer.add_transition(actions, rewards, values, log_probs, dones)
+        self._stats_kernel(rewards, dones, totals)
+
+    def _collect_graphed(self, network, vec_env, buffer, steps):
+        """The whole rollout as ONE CUDA graph, captured on first use and replayed afterwards.  Every launch of
+        the path takes its stream from torch and never synchronises, so the python loop can be captured as is;
+        the Philox counters baked into the captured launches are offset by a device-resident base that is
+        bumped before each replay, so every replay draws fresh numbers.  Removes the per-launch host overhead
+        (decisive at small batch: the reference's default is 384 envs)."""
+        key = (id(network), id(vec_env), id(buffer), steps, id(vec_env.opponent_policy))
+        if getattr(self, "_graph_key", None) != key:
+            with torch.no_grad():                          # one-time work that must not happen under capture
+                network.forward_env(vec_env.env, swap=vec_env._side)
+                opp = vec_env.opponent_policy
+                if hasattr(opp, "net"):
+                    opp.net.forward_env(vec_env.env)
+            self._graph_base = torch.zeros(1, dtype=torch.int64, device=self._dev)
+            self._graph_totals = torch.zeros(6, dtype=torch.float64, device=self._dev)
+            vec_env.counter_base = self._graph_base
+            buffer.ptr = 0
+            torch.cuda.synchronize(self._dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for _ in range(steps):
+                    self._native_step(network, vec_env, buffer, self._graph_totals, counter_base=self._graph_base)
+            self._graph, self._graph_key = graph, key
+            self._graph_replays = 0
+        else:
+            self._graph_base += 1 << 24                    # fresh counter range for this replay
+        buffer.ptr = 0
+        self._graph_totals.zero_()
+        self._graph.replay()
+        buffer.ptr = steps
+        self._graph_replays += 1
+        return self._graph_totals
+
+    def collect(self, network, vec_env, buffer: RolloutBuffer, n_steps: Optional[int] = None, graph: bool = False) -> RolloutStats:
         start = time.time()
-        if self._last_obs is None:                        # ppo.py:81-84: reset once, then carry obs across calls
-            self._last_obs, _ = vec_env.reset()
-        elif self._last_obs["observation"] is None:       # previous rollout ran on the bitboard-fed path
-            self._last_obs = vec_env.get_agent_obs()
-        obs = self._last_obs
-        totals = torch.zeros(6, dtype=torch.float64, device=self._dev)
         steps = buffer.n_steps if n_steps is None else n_steps
         packed_fast_path = hasattr(vec_env, "_side") and hasattr(buffer, "store_obs_from")
         native = packed_fast_path and hasattr(network, "forward_env")     # tcgen05 forward fed from bitboards
-        for _ in range(steps):
+        if self._last_obs is None:                        # ppo.py:81-84: reset once, then carry obs across calls
+            self._last_obs, _ = vec_env.reset(materialise=not native) if native else vec_env.reset()
+        elif self._last_obs["observation"] is None and not native:       # previous rollout ran on the bitboard-fed path
+            self._last_obs = vec_env.get_agent_obs()
+        obs = self._last_obs
+        totals = torch.zeros(6, dtype=torch.float64, device=self._dev)
+        if native and graph:
+            totals = self._collect_graphed(network, vec_env, buffer, steps)
+            steps_to_run = 0
+        else:
+            steps_to_run = steps
+        for _ in range(steps_to_run):
             if native:
-                env = vec_env.env
-                with torch.no_grad():
-                    logits, values = network.forward_env(env, swap=vec_env._side)
-                    self._calls += 1
-                    actions, log_probs, _ = masked_sample(logits, env.legal_mask(fix_all_masked=True), seed=self.seed,
-                                                          counter=self._calls, row_offset=self.row_offset)
-                buffer.store_obs_from(vec_env)
-                _, rewards, terminateds, truncateds, _ = vec_env.step(actions, materialise=False)
-                dones = terminateds | truncateds
-                buffer.add_transition(actions, rewards, values, log_probs, dones)
-                with torch.cuda.device(self._dev):
-                    check(self._L.mnk_episode_stats(_ptr(rewards), _ptr(dones), self.num_envs, _ptr(self._ep_reward),
-                                                     _ptr(self._ep_len), _ptr(totals),
-                                                     torch.cuda.current_stream(self._dev).cuda_stream), "mnk_episode_stats")
+                self._native_step(network, vec_env, buffer, totals)
                 continue
             observation, action_mask = obs["observation"], obs["action_mask"]
             with torch.no_grad():                          # ppo.py:97-100
@@ -239,14 +284,12 @@ class RolloutCollector:
                 buffer.add_transition(actions, rewards, values, log_probs, dones)
             else:
                 buffer.add(observation, actions, rewards, values, log_probs, dones, action_mask)   # ppo.py:106-108
-            with torch.cuda.device(self._dev):             # ppo.py:110-120 without host reads
-                check(self._L.mnk_episode_stats(_ptr(rewards), _ptr(dones), self.num_envs, _ptr(self._ep_reward),
-                                                 _ptr(self._ep_len), _ptr(totals),
-                                                 torch.cuda.current_stream(self._dev).cuda_stream), "mnk_episode_stats")
+            self._stats_kernel(rewards, dones, totals)
             obs = next_obs
         self._last_obs = obs if not native else {"observation": None, "action_mask": None}
         if self.world_size > 1:                            # the only collective of the rollout path
             import torch.distributed as dist_mod
+            totals = totals.clone()                        # (the graph's accumulator stays rank-local)
             dist_mod.all_reduce(totals, op=dist_mod.ReduceOp.SUM, group=self.group)
         tot = totals.tolist()                              # one device->host read per rollout
         elapsed = time.time() - start

@@ -20,9 +20,10 @@ _auto_counter = itertools.count(1)
 
 def masked_sample(logits: torch.Tensor, mask: Optional[torch.Tensor], seed: int = 0, counter: Optional[int] = None,
                   row_offset: int = 0, deterministic: bool = False, given: Optional[torch.Tensor] = None,
-                  want_log_prob: bool = True, want_entropy: bool = False
+                  want_log_prob: bool = True, want_entropy: bool = False, counter_base: Optional[torch.Tensor] = None
                   ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[torch.Tensor]]:
-    """actions i64[B], log_prob f32[B] | None, entropy f32[B] | None for Categorical(masked logits)."""
+    """actions i64[B], log_prob f32[B] | None, entropy f32[B] | None for Categorical(masked logits).
+    `counter_base`: optional device int64[1] added to `counter` on the device (CUDA-graph replays)."""
     if not logits.is_cuda:
         raise RuntimeError("mnk_b200.masked_sample: CUDA tensors only (no CPU fallback)")
     if logits.dim() != 2:
@@ -48,7 +49,7 @@ def masked_sample(logits: torch.Tensor, mask: Optional[torch.Tensor], seed: int 
     with torch.cuda.device(dev):
         rc = _lib.lib().mnk_masked_sample(
             lg.data_ptr(), lg.stride(0), None if mk is None else mk.data_ptr(), acts, rows, seed & (2**64 - 1),
-            counter & (2**64 - 1), row_offset, int(deterministic), None if given is None else given.data_ptr(),
+            counter & (2**64 - 1), None if counter_base is None else counter_base.data_ptr(), row_offset, int(deterministic), None if given is None else given.data_ptr(),
             actions.data_ptr(), None if logp is None else logp.data_ptr(), None if ent is None else ent.data_ptr(),
             torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(rc, "mnk_masked_sample")

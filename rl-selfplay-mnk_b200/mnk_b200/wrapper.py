@@ -43,7 +43,8 @@ class TorchSelfPlayWrapper:
         self.pending_resets = torch.zeros(self.num_envs, dtype=torch.bool, device=dev)    # reference :14
         self._episodes = torch.zeros(self.num_envs, dtype=torch.int32, device=dev)
         self._sp = MnkSelfplay(self._side.data_ptr(), self.pending_resets.data_ptr(), self._episodes.data_ptr(),
-                               self.seed & (2**64 - 1), env.env_offset)
+                               self.seed & (2**64 - 1), env.env_offset, None)
+        self._counter_base: Optional[torch.Tensor] = None
         self._spp = ctypes.byref(self._sp)
         self._opp_active = torch.zeros(self.num_envs, dtype=torch.uint8, device=dev)
         self._steps = 0
@@ -61,6 +62,22 @@ class TorchSelfPlayWrapper:
 
     def set_opponent(self, policy):
         self.opponent_policy = policy
+        if hasattr(policy, "counter_base"):
+            policy.counter_base = self._counter_base
+
+    @property
+    def counter_base(self) -> Optional[torch.Tensor]:
+        """Device int64[1] added on the device to the step counters of this wrapper's (and its native
+        opponent's) random draws: a CUDA graph that captured steps bakes the counters, bumping this tensor
+        between replays makes every replay draw fresh numbers (RolloutCollector.collect(graph=True))."""
+        return self._counter_base
+
+    @counter_base.setter
+    def counter_base(self, t: Optional[torch.Tensor]):
+        self._counter_base = t
+        self._sp.counter_base = None if t is None else t.data_ptr()
+        if hasattr(self.opponent_policy, "counter_base"):
+            self.opponent_policy.counter_base = t
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):

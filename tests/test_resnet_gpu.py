@@ -164,3 +164,42 @@ def test_fused_heads_match_torch_modules(m, n):
         assert logits.shape == want_l.shape and values.shape == want_v.shape
         assert torch.allclose(logits, want_l, rtol=1e-4, atol=2e-4), (logits - want_l).abs().max()
         assert torch.allclose(values, want_v, rtol=1e-4, atol=1e-5), (values - want_v).abs().max()
+
+
+@pytest.mark.parametrize("opponent_kind", ["native_nn", "random"])
+def test_graph_captured_rollout_equals_eager_rollout(opponent_kind):
+    """RolloutCollector.collect(graph=True) captures the whole rollout as one CUDA graph.  With the device
+    counter base at zero (first replay) it must reproduce the eager rollout bit for bit; the second replay
+    continues the same games with fresh random numbers."""
+    from mnk_b200 import (NativeNNPolicy, NativeResNet, RandomPolicy, ResNetActorCritic, RolloutBuffer, RolloutCollector,
+                          TorchSelfPlayWrapper, TorchVectorMnkEnv)
+    torch.manual_seed(11)
+    net = ResNetActorCritic((2, 9, 9), 81).to(DEV).eval()
+    with torch.no_grad():
+        net.policy_head[7].weight.mul_(50.0)
+    ne, steps = 384, 20                      # the reference's default env count: launch-bound when run eagerly
+    runs = []
+    for use_graph in (False, True):
+        env = TorchVectorMnkEnv(9, 9, 5, ne, device=DEV)
+        wr = TorchSelfPlayWrapper(env, seed=3)
+        wr.set_opponent(NativeNNPolicy(net, device=DEV, seed=8) if opponent_kind == "native_nn" else RandomPolicy(81))
+        agent = NativeResNet(net, device=DEV)
+        buf = RolloutBuffer(steps, ne, (2, 9, 9), 81, device=DEV, k=5)
+        col = RolloutCollector(ne, device=DEV, seed=5)
+        s1 = col.collect(agent, wr, buf, graph=use_graph)
+        first = (buf.observations.clone(), buf.actions.clone(), buf.rewards.clone(), buf.dones.clone(), buf.log_probs.clone(),
+                 s1.episodes, s1.wins)
+        buf.reset()
+        s2 = col.collect(agent, wr, buf, graph=use_graph)
+        second = (buf.observations.clone(), buf.actions.clone(), s2.episodes)
+        agent.check_error()
+        runs.append((first, second, env.state_checksum()))
+    eager, graphed = runs
+    for x, y in zip(eager[0][:5], graphed[0][:5]):
+        assert torch.equal(x, y)
+    assert eager[0][5:] == graphed[0][5:] and eager[0][5] > 0
+    # second rollout: continues from the first one's final state (same first observation as the eager run) ...
+    assert torch.equal(eager[1][0][0], graphed[1][0][0])
+    # ... with fresh draws: not a repeat of the first rollout's actions
+    assert not torch.equal(graphed[1][1], graphed[0][1])
+    assert graphed[1][2] > 0
