@@ -200,8 +200,9 @@ MNK_DEV void epilogue_row(Smem& sm, const u32* acc, const float (&bias)[NCH], in
 }
 
 __global__ void __launch_bounds__(kThreads, 2) resnet_tower_kernel(Params p) {
-    extern __shared__ unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // no pointer arithmetic through integers here: it would make every access a generic LD/ST instead of LDS/STS
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long env0 = (long long)blockIdx.x * p.spc;
     const int cells = p.m * p.n;
