@@ -295,3 +295,18 @@ def test_nnpolicy_with_stock_torch_network():
         assert bool(obs["action_mask"].gather(1, det[:, None]).all())
         obs, r, term, trunc, _ = wr.step(a)
     assert pol.act({"observation": obs["observation"][0], "action_mask": obs["action_mask"][0]}).shape == (1,)
+
+
+def test_play_batch_games_tournament_primitive():
+    """selfplay.match.play_batch_games (the fused counterpart of MatchRunner._play_batch_games,
+    src/model_comparison/match_runner.py:125-218): random vs random tic-tac-toe reproduces the
+    first-player / second-player statistics (58.5 % / 28.8 % / 12.7 %) for either colour."""
+    from selfplay.match import play_batch_games
+    from selfplay.policy import RandomPolicy
+    n = 40000
+    w, l, d = play_batch_games(RandomPolicy(9, seed=1), RandomPolicy(9, seed=2), (3, 3, 3), n, p1_is_black=True, device=DEV)
+    assert w + l + d == n
+    assert abs(w / n - 0.585) < 0.012 and abs(l / n - 0.288) < 0.012 and abs(d / n - 0.127) < 0.01
+    w, l, d = play_batch_games(RandomPolicy(9, seed=3), RandomPolicy(9, seed=4), (3, 3, 3), n, p1_is_black=False, device=DEV)
+    assert abs(w / n - 0.288) < 0.012 and abs(l / n - 0.585) < 0.012 and abs(d / n - 0.127) < 0.01
+    assert play_batch_games(None, None, (3, 3, 3), 0, True, device=DEV) == (0, 0, 0)
