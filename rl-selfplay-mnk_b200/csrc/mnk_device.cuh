@@ -265,6 +265,24 @@ MNK_DEV MoveResult apply_move(const G& g, EnvRegs<G>& s, long long action) {
     return r;
 }
 
+// only the stone placement of apply_move (no counters, no line test): what the observation / mask of the
+// post-move position needs.  Lets a second warp build the views while the first one runs the rules.
+template <class G>
+MNK_DEV void place_stone(const G& g, EnvRegs<G>& s, long long action) {
+    const bool in_range = action >= 0 && action < g.cells();
+    const int a = in_range ? (int)action : 0;
+    const int bit = a + a / g.n();
+    const int wi = bit >> 6;
+    const u64 one = in_range ? (1ull << (bit & 63)) : 0ull;
+    const bool white = (s.meta & 1u) != 0u;
+#pragma unroll
+    for (int w = 0; w < G::NW; ++w) {
+        if (w == wi) {
+            if (white) s.pl[1][w] |= one; else s.pl[0][w] |= one;
+        }
+    }
+}
+
 // guard-strided bitboard of the board's real cells (all rows' n low bits)
 template <class G>
 MNK_DEV void board_mask(const G& g, u64 (&out)[G::NW]) {
@@ -434,19 +452,20 @@ MNK_DEV u32 gather_stream_word(const u32* stage, int w) {
 template <int M, int N, int K>
 MNK_DEV void emit_block_stream(const SGeom<M, N, K>&, u32* smem, long long e0, const u64 (&obsd)[SGeom<M, N, K>::NWD],
                                const u64 (&legd)[SGeom<M, N, K>::NWL], float* __restrict__ obs,
-                               u8* __restrict__ mask) {
+                               u8* __restrict__ mask, int stage_warp = 0) {
     using TS = TileStream<SGeom<M, N, K>>;
     const int tid = threadIdx.x;
-    // 1. the compute warp stages its 32 envs
-    if (tid < 32) {
+    // 1. the warp that holds the views (lane L = env e0 + L) stages its 32 envs
+    if ((tid >> 5) == stage_warp) {
+        const int srow = tid & 31;
         if (obs != nullptr) {
-            u32* row = smem + TS::kStageO + tid * TS::OSTRIDE;
+            u32* row = smem + TS::kStageO + srow * TS::OSTRIDE;
 #pragma unroll
             for (int j = 0; j < TS::OW; ++j) row[j] = (j & 1) ? (u32)(obsd[j >> 1] >> 32) : (u32)obsd[j >> 1];
             row[TS::OW] = 0u;
         }
         if (mask != nullptr) {
-            u32* row = smem + TS::kStageL + tid * TS::LSTRIDE;
+            u32* row = smem + TS::kStageL + srow * TS::LSTRIDE;
 #pragma unroll
             for (int j = 0; j < TS::LW; ++j) row[j] = (j & 1) ? (u32)(legd[j >> 1] >> 32) : (u32)legd[j >> 1];
             row[TS::LW] = 0u;
@@ -511,8 +530,9 @@ MNK_DEV bool tile_streams(int tile_envs, const float* obs, const u8* mask) {
 
 template <class G>
 MNK_DEV void emit_block_stream_any(const G& g, u32* smem, long long e0, const u64 (&obsd)[G::NWD],
-                                   const u64 (&legd)[G::NWL], float* __restrict__ obs, u8* __restrict__ mask) {
-    if constexpr (G::kStatic) emit_block_stream(g, smem, e0, obsd, legd, obs, mask);
+                                   const u64 (&legd)[G::NWL], float* __restrict__ obs, u8* __restrict__ mask,
+                                   int stage_warp = 0) {
+    if constexpr (G::kStatic) emit_block_stream(g, smem, e0, obsd, legd, obs, mask, stage_warp);
 }
 
 // ------------------------------------------------------------------------------------------------
