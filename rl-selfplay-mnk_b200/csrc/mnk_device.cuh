@@ -326,6 +326,45 @@ MNK_DEV void build_views(const G& g, const EnvRegs<G>& s, bool swap, bool fix, u
     if (fix && !any_bit(legd)) legd[0] |= 1ull;
 }
 
+// the two halves of build_views as separate functions (for kernels that build them in different warps)
+template <class G>
+MNK_DEV void build_obs_view(const G& g, const EnvRegs<G>& s, bool swap, u64 (&obsd)[G::NWD]) {
+#pragma unroll
+    for (int w = 0; w < G::NWD; ++w) obsd[w] = 0ull;
+    const int n = g.n(), W = g.stride(), cells = g.cells();
+    auto body = [&](int r) {
+        const u32 fb = get_field(s.pl[0], r * W, n);
+        const u32 fw = get_field(s.pl[1], r * W, n);
+        or_field(obsd, r * n, swap ? fw : fb);
+        or_field(obsd, cells + r * n, swap ? fb : fw);
+    };
+    if constexpr (G::kStatic) {
+#pragma unroll
+        for (int r = 0; r < g.m(); ++r) body(r);
+    } else {
+        for (int r = 0; r < g.m(); ++r) body(r);
+    }
+}
+
+template <class G>
+MNK_DEV void build_legal_view(const G& g, const EnvRegs<G>& s, bool fix, u64 (&legd)[G::NWL]) {
+#pragma unroll
+    for (int w = 0; w < G::NWL; ++w) legd[w] = 0ull;
+    const int n = g.n(), W = g.stride();
+    const u32 rowmask = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+    u64 occ[G::NW];
+#pragma unroll
+    for (int w = 0; w < G::NW; ++w) occ[w] = s.pl[0][w] | s.pl[1][w];
+    auto body = [&](int r) { or_field(legd, r * n, ~get_field(occ, r * W, n) & rowmask); };
+    if constexpr (G::kStatic) {
+#pragma unroll
+        for (int r = 0; r < g.m(); ++r) body(r);
+    } else {
+        for (int r = 0; r < g.m(); ++r) body(r);
+    }
+    if (fix && !any_bit(legd)) legd[0] |= 1ull;
+}
+
 // inverse of the obsd half of build_views (no swap): dense 2*cells bits -> guard-strided planes
 template <class G>
 MNK_DEV void planes_from_dense(const G& g, const u64 (&obsd)[G::NWD], EnvRegs<G>& s) {
@@ -452,19 +491,20 @@ MNK_DEV u32 gather_stream_word(const u32* stage, int w) {
 template <int M, int N, int K>
 MNK_DEV void emit_block_stream(const SGeom<M, N, K>&, u32* smem, long long e0, const u64 (&obsd)[SGeom<M, N, K>::NWD],
                                const u64 (&legd)[SGeom<M, N, K>::NWL], float* __restrict__ obs,
-                               u8* __restrict__ mask, int stage_warp = 0) {
+                               u8* __restrict__ mask, int stage_warp = 0, int stage_warp_mask = -1) {
     using TS = TileStream<SGeom<M, N, K>>;
     const int tid = threadIdx.x;
-    // 1. the warp that holds the views (lane L = env e0 + L) stages its 32 envs
-    if ((tid >> 5) == stage_warp) {
+    if (stage_warp_mask < 0) stage_warp_mask = stage_warp;
+    // 1. the warp(s) holding the views (lane L = env e0 + L) stage their 32 envs
+    {
         const int srow = tid & 31;
-        if (obs != nullptr) {
+        if (obs != nullptr && (tid >> 5) == stage_warp) {
             u32* row = smem + TS::kStageO + srow * TS::OSTRIDE;
 #pragma unroll
             for (int j = 0; j < TS::OW; ++j) row[j] = (j & 1) ? (u32)(obsd[j >> 1] >> 32) : (u32)obsd[j >> 1];
             row[TS::OW] = 0u;
         }
-        if (mask != nullptr) {
+        if (mask != nullptr && (tid >> 5) == stage_warp_mask) {
             u32* row = smem + TS::kStageL + srow * TS::LSTRIDE;
 #pragma unroll
             for (int j = 0; j < TS::LW; ++j) row[j] = (j & 1) ? (u32)(legd[j >> 1] >> 32) : (u32)legd[j >> 1];
@@ -531,8 +571,8 @@ MNK_DEV bool tile_streams(int tile_envs, const float* obs, const u8* mask) {
 template <class G>
 MNK_DEV void emit_block_stream_any(const G& g, u32* smem, long long e0, const u64 (&obsd)[G::NWD],
                                    const u64 (&legd)[G::NWL], float* __restrict__ obs, u8* __restrict__ mask,
-                                   int stage_warp = 0) {
-    if constexpr (G::kStatic) emit_block_stream(g, smem, e0, obsd, legd, obs, mask, stage_warp);
+                                   int stage_warp = 0, int stage_warp_mask = -1) {
+    if constexpr (G::kStatic) emit_block_stream(g, smem, e0, obsd, legd, obs, mask, stage_warp, stage_warp_mask);
 }
 
 // ------------------------------------------------------------------------------------------------

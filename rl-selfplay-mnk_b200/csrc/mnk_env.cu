@@ -66,24 +66,26 @@ step_dense_kernel(G g, mnk_state_t st, const void* __restrict__ actions, float* 
             if (illegal != nullptr && r.illegal) note_illegal(illegal, e);
             if (emit && !stream) build_views(g, s, false, false, obsd, legd);
             if ((flags & MNK_STEP_AUTORESET) && r.done) env_zero(s);
-            if (stream) asm volatile("bar.sync 2, 64;" ::: "memory");   // the views warp has read the pre-move state
+            if (stream) asm volatile("bar.sync 2, 96;" ::: "memory");   // the views warps have read the pre-move state
             env_store(st, e, s);
         }
         if (emit && !stream) emit_tile(g, e0, tile_envs, lane, obsd, legd, obs, mask);
-    } else if (warp == 1 && stream) {
-        // the views warp (stream path only: full 32-env tile): in parallel with the rules warp it reads the tile's
-        // PRE-move state, places the stone and builds the dense views, taking ~240 of the ~400 serial
-        // instructions off the tile's critical path.  Named barrier 2 orders its loads before warp 0's store.
+    } else if (warp <= 2 && stream) {
+        // the views warps (stream path only: full 32-env tile): in parallel with the rules warp they read the
+        // tile's PRE-move state, place the stone and build the dense views -- warp 1 the observation bits,
+        // warp 2 the legal-cell bits -- which takes ~240 of the ~400 serial instructions off the tile's critical
+        // path.  Named barrier 2 orders their loads before warp 0's store.
         const long long e = e0 + lane;
         EnvRegs<G> s;
         env_load(st, e, s);
         const long long a = ACT32 ? (long long)static_cast<const int32_t*>(actions)[e]
                                   : (long long)static_cast<const int64_t*>(actions)[e];
-        asm volatile("bar.arrive 2, 64;" ::: "memory");
+        asm volatile("bar.arrive 2, 96;" ::: "memory");
         place_stone(g, s, a);
-        build_views(g, s, false, false, obsd, legd);
+        if (warp == 1) build_obs_view(g, s, false, obsd);
+        else build_legal_view(g, s, false, legd);
     }
-    if (stream) emit_block_stream_any(g, tile_smem, e0, obsd, legd, obs, mask, 1);
+    if (stream) emit_block_stream_any(g, tile_smem, e0, obsd, legd, obs, mask, 1, 2);
 }
 
 // ------------------------------------------------------------------------------------------------
