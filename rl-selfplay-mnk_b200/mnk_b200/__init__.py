@@ -14,8 +14,8 @@ from .rollout import RolloutBuffer, RolloutCollector, RolloutStats  # noqa: F401
 from .nets import ResNetActorCritic  # noqa: F401
 from .resnet import NativeNNPolicy, NativeResNet  # noqa: F401
 from .ppo import PPOAgent, TrainingMetrics  # noqa: F401
-from . import dist  # noqa: F401
+from . import dist, model_io  # noqa: F401
 
 __all__ = ["build", "lib", "LIB_PATH", "TorchVectorMnkEnv", "TorchSelfPlayWrapper", "Policy", "RandomPolicy", "NNPolicy",
-           "MaskedCategorical", "masked_sample", "RolloutBuffer", "RolloutCollector", "RolloutStats", "dist",
+           "MaskedCategorical", "masked_sample", "RolloutBuffer", "RolloutCollector", "RolloutStats", "dist", "model_io",
            "ResNetActorCritic", "NativeResNet", "NativeNNPolicy", "PPOAgent", "TrainingMetrics"]
