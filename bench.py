@@ -54,20 +54,21 @@ WORKLOADS = {
     "cfg5": (19, 19, 5, lambda n: 4194304 // 8, "cfg5: 19x19x5, 524,288 envs/GPU (4,194,304 over 8 GPUs)", "weak"),
 }
 SCALING = "weak"
-M = N_COLS = K_LINE = CELLS = ENVS_PER_GPU = ALG_BYTES_PER_ENV_STEP = 0
+M = N_COLS = K_LINE = CELLS = ENVS_PER_GPU = ALG_BYTES_PER_ENV_STEP = PACKED_BYTES_PER_ENV_STEP = 0
 WORKLOAD_DESC = ""
 
 
 def configure(name: str, gpus: int, envs_override=None):
     """Sets the board geometry, per-GPU env count and the algorithmic bytes per env-step (SURVEY 8d:
     8 B action + 2 x packed state + f32 observation + bool mask + reward/done)."""
-    global M, N_COLS, K_LINE, CELLS, ENVS_PER_GPU, ALG_BYTES_PER_ENV_STEP, WORKLOAD_DESC, METRIC, SCALING
+    global M, N_COLS, K_LINE, CELLS, ENVS_PER_GPU, ALG_BYTES_PER_ENV_STEP, PACKED_BYTES_PER_ENV_STEP, WORKLOAD_DESC, METRIC, SCALING
     M, N_COLS, K_LINE, envs_fn, WORKLOAD_DESC, SCALING = WORKLOADS[name]
     CELLS = M * N_COLS
     ENVS_PER_GPU = envs_override or envs_fn(gpus)
     words = (M * (N_COLS + 1) + 63) // 64
     state_bytes = 2 * 8 * words + 4
     ALG_BYTES_PER_ENV_STEP = 8 + 2 * state_bytes + 8 * CELLS + CELLS + 5      # 814 at 9x9
+    PACKED_BYTES_PER_ENV_STEP = 8 + 2 * state_bytes + 5                       # 85 at 9x9
     METRIC = f"env steps/sec ({M}x{N_COLS}x{K_LINE}, win-check)"
 
 
@@ -147,28 +148,32 @@ def profiled_traffic():
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm (oracle/torch_port.py on the host cores)
 # ------------------------------------------------------------------------------------------------
-def cpu_port_run(actions_cpu, envs, warmup, steps, budget_s, check_state=None, init_state=None):
+def cpu_port_run(actions_cpu, envs, warmup, steps, budget_s, check_state=None, init_state=None, device="cpu"):
     """Replays `actions_cpu[t]` ([T, envs] int64 legal actions, or None => draw them with the
     reference's RandomPolicy arithmetic outside the timed sections) through the torch-op port.
     Times only port_step + port_reset(done_idx), like the reference harness of SURVEY 8d."""
     import torch
     from oracle import torch_port as tp
     torch.set_num_threads(os.cpu_count() or 1)
-    s = tp.port_make(M, N_COLS, K_LINE, envs)
+    s = tp.port_make(M, N_COLS, K_LINE, envs, device=device)
     obs = tp.port_reset(s)
     if init_state is not None:          # start from the same mid-game positions as the B200 arm
         s.planes.copy_(init_state[0]), s.to_move.copy_(init_state[1]), s.plies.copy_(init_state[2])
         obs = tp.port_observe(s)
+    on_gpu = str(device) != "cpu"
+    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
     timed, done_steps = 0.0, 0
     t_begin = time.perf_counter()
     total = warmup + steps
     for t in range(total):
         a = actions_cpu[t] if actions_cpu is not None else tp.port_uniform_legal(obs["action_mask"])
+        sync()
         t0 = time.perf_counter()
         obs, r, d = tp.port_step(s, a)
         idx = torch.nonzero(d).squeeze(1)
         if idx.numel():
             obs = tp.port_reset(s, idx)
+        sync()
         dt = time.perf_counter() - t0
         if t >= warmup:
             timed += dt
@@ -325,6 +330,33 @@ def run_b200_arm(args):
     ms_eager = ev0.elapsed_time(ev1)
     verified = verified and env.state_checksum() == want_digest
 
+    # ---- packed mode: the same K steps without materialising observation / mask ---------------
+    def launch_packed(t, stream_):
+        rc = L.mnk_step(env._stp, actions[t].data_ptr(), None, envs, rewards.data_ptr(), dones.data_ptr(),
+                        None, None, None, flags, stream_)
+        _lib.check(rc, "mnk_step")
+
+    env._bits.copy_(warm_bits)
+    env._meta.copy_(warm_meta)
+    graph_p = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph_p, stream=side):
+            for t in range(W, total):
+                launch_packed(t, side.cuda_stream)
+    torch.cuda.current_stream().wait_stream(side)
+    graph_p.replay()
+    torch.cuda.synchronize()
+    env._bits.copy_(warm_bits)
+    env._meta.copy_(warm_meta)
+    barrier()
+    ev0.record()
+    graph_p.replay()
+    ev1.record()
+    barrier()
+    ms_packed = ev0.elapsed_time(ev1)
+    verified = verified and env.state_checksum() == want_digest
+
     # ---- e2e: host buffers through the public API -----------------------------------------------------
     e2e_steps = min(K, args.e2e_steps)
     host_actions = torch.empty((W + e2e_steps, envs), dtype=torch.long).pin_memory()
@@ -353,13 +385,13 @@ def run_b200_arm(args):
     clocks = sampler.stop()
 
     # ---- reduce over ranks -------------------------------------------------------------------------
-    times = torch.tensor([ms, ms_eager, e2e_ms, e2e_copy_ms, e2e_zc_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([ms, ms_eager, e2e_ms, e2e_copy_ms, e2e_zc_ms, ms_packed], dtype=torch.float64, device=dev)
     ok = torch.tensor([1.0 if verified else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)          # end-of-run statistics over NCCL
-    ms, ms_eager, e2e_ms, e2e_copy_ms, e2e_zc_ms = (float(x) for x in times.tolist())
+    ms, ms_eager, e2e_ms, e2e_copy_ms, e2e_zc_ms, ms_packed = (float(x) for x in times.tolist())
     verified = bool(ok.item() == 1.0)
 
     if rank == 0:
@@ -390,6 +422,11 @@ def run_b200_arm(args):
                            "stream synchronised every step; value = the faster of the two transports",
                     "staged_copies": total_envs * e2e_steps / (e2e_copy_ms * 1e-3),
                     "zero_copy": total_envs * e2e_steps / (e2e_zc_ms * 1e-3)},
+            "packed_mode": {"value": total_envs * K / (ms_packed * 1e-3), "unit": UNIT, "launch_us": 1e3 * ms_packed / K,
+                            "alg_bytes_per_env_step": PACKED_BYTES_PER_ENV_STEP,
+                            "hbm_frac": PACKED_BYTES_PER_ENV_STEP * envs / (1e3 * ms_packed / K * 1e-6) / 1e9 / peak,
+                            "note": "same K steps, observation / mask not materialised (state + action + reward / done "
+                                    "traffic only); latency-bound, reported for SURVEY 8d, not the headline"},
             "gpu_launches": K,
             "clocks": clocks,
             "stats": {"episodes": stats[0].item(), "wins": stats[1].item(), "plies": stats[2].item()},
@@ -416,6 +453,14 @@ def run_b200_arm(args):
                 "sample": f"first {res['steps']} steps of the same action trace, all {envs} envs, oracle/torch_port.py "
                           f"(reference torch op sequence) on {os.cpu_count()} host CPUs",
                 "parity_with_gpu_state": res["parity"]}
+            # informative second baseline: the same torch op sequence on this B200 (device="cuda")
+            gsteps = min(args.cpu_steps, 40)
+            gres = cpu_port_run(actions, envs, min(W, 3), gsteps - min(W, 3), 60.0, None,
+                                tuple(x.to(dev) for x in init), device=dev)
+            line["cpu_baseline"]["stock_torch_same_gpu"] = {
+                "value": gres["value"], "unit": UNIT, "steps": gres["steps"],
+                "note": "oracle/torch_port.py with device='cuda' (stock PyTorch kernels, as the reference would run on "
+                        "this GPU), same trace, host-synchronised per step like the reference's loop"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -39,17 +39,19 @@ class PortState:
     w_diag: torch.Tensor      # [eye ; fliplr(eye)] [2,1,k,k]  (:30-32)
 
 
-def port_make(m: int, n: int, k: int, num_envs: int) -> PortState:
+def port_make(m: int, n: int, k: int, num_envs: int, device="cpu") -> PortState:
+    """`device="cuda"` runs the same torch op sequence on the GPU (the reference's own `device`
+    argument, :8-16) -- bench.py's informative "stock PyTorch on the same B200" figure."""
     assert m >= k and n >= k
-    eye = torch.eye(k)
+    eye = torch.eye(k, device=device)
     return PortState(
         m, n, k, num_envs,
-        planes=torch.zeros((num_envs, 2, m, n), dtype=torch.float32),
-        to_move=torch.zeros(num_envs, dtype=torch.long),
-        plies=torch.zeros(num_envs, dtype=torch.long),
-        everyone=torch.arange(num_envs),
-        w_row=torch.ones((1, 1, 1, k)),
-        w_col=torch.ones((1, 1, k, 1)),
+        planes=torch.zeros((num_envs, 2, m, n), dtype=torch.float32, device=device),
+        to_move=torch.zeros(num_envs, dtype=torch.long, device=device),
+        plies=torch.zeros(num_envs, dtype=torch.long, device=device),
+        everyone=torch.arange(num_envs, device=device),
+        w_row=torch.ones((1, 1, 1, k), device=device),
+        w_col=torch.ones((1, 1, k, 1), device=device),
         w_diag=torch.stack([eye, torch.fliplr(eye)]).reshape(2, 1, k, k),
     )
 
@@ -87,10 +89,10 @@ def port_step_subset(s: PortState, actions: torch.Tensor, which: torch.Tensor) -
     s.plies[which] += 1
     won = _line_found(s, which, movers)
     drawn = (s.plies[which] >= s.m * s.n) & (~won)
-    rewards = torch.zeros(s.num_envs)
+    rewards = torch.zeros(s.num_envs, device=s.planes.device)
     if won.any():
         rewards[which[won]] = 1.0
-    dones = torch.zeros(s.num_envs, dtype=torch.bool)
+    dones = torch.zeros(s.num_envs, dtype=torch.bool, device=s.planes.device)
     dones[which] = won | drawn
     s.to_move[which] ^= 1
     return port_observe(s), rewards, dones

@@ -1,5 +1,7 @@
 // mnk_dispatch.cuh -- host-side helpers: argument validation, geometry dispatch, launch shapes.
 #pragma once
+#include <atomic>
+
 #include "mnk_device.cuh"
 
 // Geometries compiled with every loop bound and shift distance constant.  Anything else runs the
@@ -47,6 +49,25 @@ static inline int mnk_dispatch_geom(const mnk_state_t& st, F&& f) {
 static inline int mnk_launch_status() {
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MNK_OK : (int)e;
+}
+
+// Opt-in dynamic shared memory is a per-device function attribute.  `granted` (one slot per device,
+// zero-initialised by the caller as a function-local static) remembers the largest size already set on
+// each device, so a process driving several GPUs configures each of them and concurrent callers at
+// worst repeat an idempotent call.
+constexpr int kMaxDevices = 64;
+template <class Kernel>
+static inline int mnk_optin_smem(Kernel kernel, size_t bytes, std::atomic<size_t>* granted) {
+    if (bytes <= 48 * 1024) return MNK_OK;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    const bool tracked = dev >= 0 && dev < kMaxDevices;
+    if (tracked && granted[dev].load(std::memory_order_relaxed) >= bytes) return MNK_OK;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    if (tracked) granted[dev].store(bytes, std::memory_order_relaxed);
+    return MNK_OK;
 }
 
 // warp-tile kernels (pack): one warp per 32 consecutive envs, 4 warps per CTA

@@ -30,37 +30,40 @@ MNK_DEV float warp_sum(float v) {
 // registers once (the k-major layout makes lane-strided shared-memory passes 16-way bank conflicted).
 constexpr int kMaxItems = 24;    // per lane: covers len <= 768 (19x19: 2A = 722)
 
-MNK_DEV void layernorm_relu_regs(float (&v)[kMaxItems], int len, const float* __restrict__ gamma,
+template <int kItems>
+MNK_DEV void layernorm_relu_regs(float (&v)[kItems], int len, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float* x, int s, int lane) {
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxItems; ++i) sum += (lane + 32 * i < len) ? v[i] : 0.f;
+    for (int i = 0; i < kItems; ++i) sum += (lane + 32 * i < len) ? v[i] : 0.f;
     const float mean = warp_sum(sum) / (float)len;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxItems; ++i) {
+    for (int i = 0; i < kItems; ++i) {
         const float d = (lane + 32 * i < len) ? v[i] - mean : 0.f;
         sq += d * d;
     }
     const float rstd = rsqrtf(warp_sum(sq) / (float)len + kEps);
 #pragma unroll
-    for (int i = 0; i < kMaxItems; ++i) {
+    for (int i = 0; i < kItems; ++i) {
         const int k = lane + 32 * i;
         if (k < len) x[k * kSB + s] = fmaxf((v[i] - mean) * rstd * __ldg(gamma + k) + __ldg(beta + k), 0.f);
     }
 }
 
-// source = global row (coalesced) or the k-major shared-memory column of sample s
+// source = global row (coalesced) or the k-major shared-memory column of sample s.  kItems = register
+// slots per lane the caller guarantees to be enough (len <= 32 * kItems) -- 0 = unknown, shared-memory passes.
+template <int kItems>
 MNK_DEV void layernorm_relu(const float* __restrict__ grow, bool live, float* x, int s, int len,
                             const float* __restrict__ gamma, const float* __restrict__ beta, int lane) {
-    if (len <= 32 * kMaxItems) {
-        float v[kMaxItems];
+    if constexpr (kItems > 0) {
+        float v[kItems];
 #pragma unroll
-        for (int i = 0; i < kMaxItems; ++i) {
+        for (int i = 0; i < kItems; ++i) {
             const int k = lane + 32 * i;
             v[i] = (k < len) ? (grow ? (live ? __ldg(grow + k) : 0.f) : x[k * kSB + s]) : 0.f;
         }
-        layernorm_relu_regs(v, len, gamma, beta, x, s, lane);
+        layernorm_relu_regs<kItems>(v, len, gamma, beta, x, s, lane);
         return;
     }
     // very large boards: shared-memory passes
@@ -81,27 +84,45 @@ MNK_DEV void layernorm_relu(const float* __restrict__ grow, bool live, float* x,
 }
 
 // out[j][8 samples] = bias[j] + sum_k wT[k][j] * x[k][samples]   for j = unit, samples = 8*half .. 8*half+7
+// The weight column is walked four k at a time with the NEXT four weights already in flight while the
+// current 32 FMAs issue (the loads are L1 / L2 hits whose latency was the kernel's top stall).  Past the
+// end, weights are zero and the activation index is clamped (never multiplies stale shared memory).
 MNK_DEV void dense8(const float* __restrict__ wT, int ld, const float* __restrict__ bias, const float* x, int len, int unit,
                     int half, float (&acc)[8]) {
     const float b = __ldg(bias + unit);
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = b;
     const float4* xv = reinterpret_cast<const float4*>(x) + 2 * half;      // x[k*16 + 8*half ..]
-#pragma unroll 4
-    for (int k = 0; k < len; ++k) {
-        const float w = __ldg(wT + (size_t)k * ld + unit);
-        const float4 v0 = xv[4 * k], v1 = xv[4 * k + 1];
-        acc[0] = fmaf(w, v0.x, acc[0]);
-        acc[1] = fmaf(w, v0.y, acc[1]);
-        acc[2] = fmaf(w, v0.z, acc[2]);
-        acc[3] = fmaf(w, v0.w, acc[3]);
-        acc[4] = fmaf(w, v1.x, acc[4]);
-        acc[5] = fmaf(w, v1.y, acc[5]);
-        acc[6] = fmaf(w, v1.z, acc[6]);
-        acc[7] = fmaf(w, v1.w, acc[7]);
+    const float* wcol = wT + unit;
+    float wn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wn[j] = (j < len) ? __ldg(wcol + (size_t)j * ld) : 0.f;
+    for (int k0 = 0; k0 < len; k0 += 4) {
+        float w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            w[j] = wn[j];
+            const int kn = k0 + 4 + j;
+            wn[j] = (kn < len) ? __ldg(wcol + (size_t)kn * ld) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = min(k0 + j, len - 1);
+            const float4 v0 = xv[4 * k], v1 = xv[4 * k + 1];
+            acc[0] = fmaf(w[j], v0.x, acc[0]);
+            acc[1] = fmaf(w[j], v0.y, acc[1]);
+            acc[2] = fmaf(w[j], v0.z, acc[2]);
+            acc[3] = fmaf(w[j], v0.w, acc[3]);
+            acc[4] = fmaf(w[j], v1.x, acc[4]);
+            acc[5] = fmaf(w[j], v1.y, acc[5]);
+            acc[6] = fmaf(w[j], v1.z, acc[6]);
+            acc[7] = fmaf(w[j], v1.w, acc[7]);
+        }
     }
 }
 
+// kItems: register slots per lane for the policy features (2A <= 32 * kItems); the value features use half.
+template <int kItems>
 __global__ void __launch_bounds__(kThreads)
 heads_kernel(const float* __restrict__ pf, const float* __restrict__ vf, long long rows, int cells, mnk_heads_weights_t w,
              float* __restrict__ logits, float* __restrict__ values) {
@@ -122,8 +143,8 @@ heads_kernel(const float* __restrict__ pf, const float* __restrict__ vf, long lo
             const long long r = r0 + sidx;
             const bool live = r < rows;
             const long long rr = live ? r : 0;
-            layernorm_relu(pf + (size_t)rr * two, live, xp, sidx, two, w.p_ln1_w, w.p_ln1_b, lane);
-            layernorm_relu(vf + (size_t)rr * cells, live, xv, sidx, cells, w.v_ln1_w, w.v_ln1_b, lane);
+            layernorm_relu<kItems>(pf + (size_t)rr * two, live, xp, sidx, two, w.p_ln1_w, w.p_ln1_b, lane);
+            layernorm_relu<(kItems + 1) / 2>(vf + (size_t)rr * cells, live, xv, sidx, cells, w.v_ln1_w, w.v_ln1_b, lane);
         }
         __syncthreads();
         // 2. first Linear of both heads: thread = (hidden unit, 8 samples)
@@ -142,8 +163,8 @@ heads_kernel(const float* __restrict__ pf, const float* __restrict__ vf, long lo
         // 3. LayerNorm(128) + ReLU per sample
 #pragma unroll
         for (int rep = 0; rep < 2; ++rep) {
-            layernorm_relu(nullptr, true, hp, warp + 8 * rep, kH, w.p_ln2_w, w.p_ln2_b, lane);
-            layernorm_relu(nullptr, true, hv, warp + 8 * rep, kH, w.v_ln2_w, w.v_ln2_b, lane);
+            layernorm_relu<kH / 32>(nullptr, true, hp, warp + 8 * rep, kH, w.p_ln2_w, w.p_ln2_b, lane);
+            layernorm_relu<kH / 32>(nullptr, true, hv, warp + 8 * rep, kH, w.v_ln2_w, w.v_ln2_b, lane);
         }
         __syncthreads();
         // 4. output layers: logits (thread = (cell, 8 samples)), value (warp = 2 samples)
@@ -179,15 +200,24 @@ extern "C" int mnk_resnet_heads(const float* policy_feat, const float* value_fea
     if (rows < 0 || cells < 1 || cells > 1024) return MNK_ERR_ARG;
     if (rows == 0) return MNK_OK;
     const size_t smem = sizeof(float) * hd::kSB * (size_t)(3 * cells + 2 * hd::kH);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(hd::heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
     const long long batches = (rows + hd::kSB - 1) / hd::kSB;
-    const unsigned grid = (unsigned)(batches < 148 * 4 ? batches : 148 * 4);
-    hd::heads_kernel<<<grid, hd::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(policy_feat, value_feat, rows, cells, *w,
-                                                                                     logits, values);
-    return mnk_launch_status();
+    auto launch = [&](auto kernel, std::atomic<size_t>* granted) {
+        if (int rc = mnk_optin_smem(kernel, smem, granted)) return rc;
+        // persistent grid: exactly the CTAs that are resident at once on the 148 SMs (one wave, no tail)
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, hd::kThreads, smem);
+        if (e != cudaSuccess) return (int)e;
+        const long long resident = 148LL * (per_sm > 0 ? per_sm : 1);
+        const unsigned grid = (unsigned)(batches < resident ? batches : resident);
+        kernel<<<grid, hd::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(policy_feat, value_feat, rows, cells, *w, logits,
+                                                                                values);
+        return mnk_launch_status();
+    };
+    static std::atomic<size_t> granted[5][kMaxDevices];
+    const int items = (2 * cells + 31) / 32;       // LayerNorm register slots per lane
+    if (items <= 6) return launch(hd::heads_kernel<6>, granted[0]);      // up to 9x9 (2A = 162)
+    if (items <= 11) return launch(hd::heads_kernel<11>, granted[1]);    // 13x13 (338)
+    if (items <= 15) return launch(hd::heads_kernel<15>, granted[2]);    // 15x15 (450)
+    if (items <= hd::kMaxItems) return launch(hd::heads_kernel<hd::kMaxItems>, granted[3]);   // 19x19 (722)
+    return launch(hd::heads_kernel<0>, granted[4]);                      // larger: shared-memory passes
 }

@@ -386,12 +386,8 @@ extern "C" int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, cons
     p.swap = swap; p.weights = static_cast<const unsigned char*>(weights); p.bias = bias;
     p.head_w = head_w; p.head_b = head_b; p.policy_feat = policy_feat; p.value_feat = value_feat; p.error = error;
     const size_t smem = sizeof(rn::Smem) + 128;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rn::resnet_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static std::atomic<size_t> granted[kMaxDevices];
+    if (int rc = mnk_optin_smem(rn::resnet_tower_kernel, smem, granted)) return rc;
     const unsigned grid = (unsigned)((st->num_envs + p.spc - 1) / p.spc);
     rn::resnet_tower_kernel<<<grid, rn::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     return mnk_launch_status();
