@@ -53,7 +53,7 @@ MNK_DEV void layernorm_relu_regs(float (&v)[kItems], int len, const float* __res
 
 // source = global row (coalesced) or the k-major shared-memory column of sample s.  kItems = register
 // slots per lane the caller guarantees to be enough (len <= 32 * kItems) -- 0 = unknown, shared-memory passes.
-template <int kItems>
+template <int kItems, bool kFromGlobal>
 MNK_DEV void layernorm_relu(const float* __restrict__ grow, bool live, float* x, int s, int len,
                             const float* __restrict__ gamma, const float* __restrict__ beta, int lane) {
     if constexpr (kItems > 0) {
@@ -61,13 +61,16 @@ MNK_DEV void layernorm_relu(const float* __restrict__ grow, bool live, float* x,
 #pragma unroll
         for (int i = 0; i < kItems; ++i) {
             const int k = lane + 32 * i;
-            v[i] = (k < len) ? (grow ? (live ? __ldg(grow + k) : 0.f) : x[k * kSB + s]) : 0.f;
+            if constexpr (kFromGlobal)
+                v[i] = (k < len && live) ? __ldg(grow + k) : 0.f;
+            else
+                v[i] = (k < len) ? x[k * kSB + s] : 0.f;
         }
         layernorm_relu_regs<kItems>(v, len, gamma, beta, x, s, lane);
         return;
     }
     // very large boards: shared-memory passes
-    if (grow)
+    if constexpr (kFromGlobal)
         for (int k = lane; k < len; k += 32) x[k * kSB + s] = live ? __ldg(grow + k) : 0.f;
     __syncwarp();
     float sum = 0.f;
@@ -84,40 +87,72 @@ MNK_DEV void layernorm_relu(const float* __restrict__ grow, bool live, float* x,
 }
 
 // out[j][8 samples] = bias[j] + sum_k wT[k][j] * x[k][samples]   for j = unit, samples = 8*half .. 8*half+7
-// The weight column is walked four k at a time with the NEXT four weights already in flight while the
-// current 32 FMAs issue (the loads are L1 / L2 hits whose latency was the kernel's top stall).  Past the
-// end, weights are zero and the activation index is clamped (never multiplies stale shared memory).
+// The weight column is walked in groups of four k with the NEXT group's weights already in flight while the
+// current 32 FMAs issue (the loads are L1 / L2 hits whose latency was the kernel's top stall); two register
+// sets alternate so that nothing is moved, the steady-state loop carries no predicates or index clamps
+// (47 instructions per 32 FMAs), and the last groups / the len % 4 tail are peeled.
+MNK_DEV void fma_group(const float (&w)[4], const float4* __restrict__ xv, float (&acc)[8]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 v0 = xv[4 * j], v1 = xv[4 * j + 1];
+        acc[0] = fmaf(w[j], v0.x, acc[0]);
+        acc[1] = fmaf(w[j], v0.y, acc[1]);
+        acc[2] = fmaf(w[j], v0.z, acc[2]);
+        acc[3] = fmaf(w[j], v0.w, acc[3]);
+        acc[4] = fmaf(w[j], v1.x, acc[4]);
+        acc[5] = fmaf(w[j], v1.y, acc[5]);
+        acc[6] = fmaf(w[j], v1.z, acc[6]);
+        acc[7] = fmaf(w[j], v1.w, acc[7]);
+    }
+}
+
+MNK_DEV void load_group(float (&w)[4], const float* __restrict__ wp, int ld) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = __ldg(wp + (size_t)j * ld);
+}
+
 MNK_DEV void dense8(const float* __restrict__ wT, int ld, const float* __restrict__ bias, const float* x, int len, int unit,
                     int half, float (&acc)[8]) {
     const float b = __ldg(bias + unit);
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = b;
-    const float4* xv = reinterpret_cast<const float4*>(x) + 2 * half;      // x[k*16 + 8*half ..]
-    const float* wcol = wT + unit;
-    float wn[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) wn[j] = (j < len) ? __ldg(wcol + (size_t)j * ld) : 0.f;
-    for (int k0 = 0; k0 < len; k0 += 4) {
-        float w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            w[j] = wn[j];
-            const int kn = k0 + 4 + j;
-            wn[j] = (kn < len) ? __ldg(wcol + (size_t)kn * ld) : 0.f;
+    const float4* xv = reinterpret_cast<const float4*>(x) + 2 * half;      // x[k*16 + 8*half ..]: 4 float4 per k
+    const float* wp = wT + unit;
+    const size_t step = (size_t)4 * ld;
+    int groups = len >> 2;
+    if (groups > 0) {
+        float wa[4], wb[4];
+        load_group(wa, wp, ld);
+        while (groups >= 3) {              // groups g, g+1 computed; g+1, g+2 fetched
+            load_group(wb, wp + step, ld);
+            fma_group(wa, xv, acc);
+            load_group(wa, wp + 2 * step, ld);
+            fma_group(wb, xv + 16, acc);
+            wp += 2 * step;
+            xv += 32;
+            groups -= 2;
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = min(k0 + j, len - 1);
-            const float4 v0 = xv[4 * k], v1 = xv[4 * k + 1];
-            acc[0] = fmaf(w[j], v0.x, acc[0]);
-            acc[1] = fmaf(w[j], v0.y, acc[1]);
-            acc[2] = fmaf(w[j], v0.z, acc[2]);
-            acc[3] = fmaf(w[j], v0.w, acc[3]);
-            acc[4] = fmaf(w[j], v1.x, acc[4]);
-            acc[5] = fmaf(w[j], v1.y, acc[5]);
-            acc[6] = fmaf(w[j], v1.z, acc[6]);
-            acc[7] = fmaf(w[j], v1.w, acc[7]);
+        if (groups == 2) {
+            load_group(wb, wp + step, ld);
+            fma_group(wa, xv, acc);
+            fma_group(wb, xv + 16, acc);
+        } else {
+            fma_group(wa, xv, acc);
         }
+        wp += (size_t)groups * step;
+        xv += 16 * groups;
+    }
+    for (int k = len & ~3; k < len; ++k, wp += ld, xv += 4) {
+        const float w = __ldg(wp);
+        const float4 v0 = xv[0], v1 = xv[1];
+        acc[0] = fmaf(w, v0.x, acc[0]);
+        acc[1] = fmaf(w, v0.y, acc[1]);
+        acc[2] = fmaf(w, v0.z, acc[2]);
+        acc[3] = fmaf(w, v0.w, acc[3]);
+        acc[4] = fmaf(w, v1.x, acc[4]);
+        acc[5] = fmaf(w, v1.y, acc[5]);
+        acc[6] = fmaf(w, v1.z, acc[6]);
+        acc[7] = fmaf(w, v1.w, acc[7]);
     }
 }
 
@@ -143,8 +178,8 @@ heads_kernel(const float* __restrict__ pf, const float* __restrict__ vf, long lo
             const long long r = r0 + sidx;
             const bool live = r < rows;
             const long long rr = live ? r : 0;
-            layernorm_relu<kItems>(pf + (size_t)rr * two, live, xp, sidx, two, w.p_ln1_w, w.p_ln1_b, lane);
-            layernorm_relu<(kItems + 1) / 2>(vf + (size_t)rr * cells, live, xv, sidx, cells, w.v_ln1_w, w.v_ln1_b, lane);
+            layernorm_relu<kItems, true>(pf + (size_t)rr * two, live, xp, sidx, two, w.p_ln1_w, w.p_ln1_b, lane);
+            layernorm_relu<(kItems + 1) / 2, true>(vf + (size_t)rr * cells, live, xv, sidx, cells, w.v_ln1_w, w.v_ln1_b, lane);
         }
         __syncthreads();
         // 2. first Linear of both heads: thread = (hidden unit, 8 samples)
@@ -163,8 +198,8 @@ heads_kernel(const float* __restrict__ pf, const float* __restrict__ vf, long lo
         // 3. LayerNorm(128) + ReLU per sample
 #pragma unroll
         for (int rep = 0; rep < 2; ++rep) {
-            layernorm_relu<kH / 32>(nullptr, true, hp, warp + 8 * rep, kH, w.p_ln2_w, w.p_ln2_b, lane);
-            layernorm_relu<kH / 32>(nullptr, true, hv, warp + 8 * rep, kH, w.v_ln2_w, w.v_ln2_b, lane);
+            layernorm_relu<kH / 32, false>(nullptr, true, hp, warp + 8 * rep, kH, w.p_ln2_w, w.p_ln2_b, lane);
+            layernorm_relu<kH / 32, false>(nullptr, true, hv, warp + 8 * rep, kH, w.v_ln2_w, w.v_ln2_b, lane);
         }
         __syncthreads();
         // 4. output layers: logits (thread = (cell, 8 samples)), value (warp = 2 samples)
