@@ -232,7 +232,9 @@ int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, const void* wei
 /* The heads' tails after the tower (resnet.py:41-63), one kernel, fp32:
  *   logits = Linear(128,A)(ReLU(LN(128)(Linear(2A,128)(ReLU(LN(2A)(policy_feat))))))
  *   values = Tanh(Linear(128,1)(ReLU(LN(128)(Linear(A,128)(ReLU(LN(A)(value_feat)))))))
- * Linear weights are passed TRANSPOSED ([in][out], contiguous); hidden width is 128. */
+ * Linear weights are passed TRANSPOSED ([in][out], contiguous); hidden width is 128.
+ * `values` may be NULL (then `value_feat` may be too): the value head is skipped -- a policy-only caller such
+ * as the frozen opponent (src/selfplay/policy.py:45-52 discards the value). */
 typedef struct mnk_heads_weights {
     const float *p_ln1_w, *p_ln1_b; /* [2A]                         */
     const float *p_w1t, *p_b1;      /* [2A][128], [128]             */

@@ -169,6 +169,7 @@ heads_kernel(const float* __restrict__ pf, const float* __restrict__ vf, long lo
     float* hv = hp + kH * kSB;              // [128][8] value hidden
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int unit = tid & (kH - 1), half = tid >> 7;
+    const bool want_value = values != nullptr;       // policy-only callers (the opponent) skip the value head
 
     for (long long r0 = (long long)blockIdx.x * kSB; r0 < rows; r0 += (long long)gridDim.x * kSB) {
         // 1. load (coalesced per sample row) + LayerNorm + ReLU; rows past the end are zero-filled
@@ -179,7 +180,8 @@ heads_kernel(const float* __restrict__ pf, const float* __restrict__ vf, long lo
             const bool live = r < rows;
             const long long rr = live ? r : 0;
             layernorm_relu<kItems, true>(pf + (size_t)rr * two, live, xp, sidx, two, w.p_ln1_w, w.p_ln1_b, lane);
-            layernorm_relu<(kItems + 1) / 2, true>(vf + (size_t)rr * cells, live, xv, sidx, cells, w.v_ln1_w, w.v_ln1_b, lane);
+            if (want_value)
+                layernorm_relu<(kItems + 1) / 2, true>(vf + (size_t)rr * cells, live, xv, sidx, cells, w.v_ln1_w, w.v_ln1_b, lane);
         }
         __syncthreads();
         // 2. first Linear of both heads: thread = (hidden unit, 8 samples)
@@ -189,17 +191,19 @@ heads_kernel(const float* __restrict__ pf, const float* __restrict__ vf, long lo
             float4* dst = reinterpret_cast<float4*>(hp + unit * kSB + 8 * half);
             dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
             dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            dense8(w.v_w1t, kH, w.v_b1, xv, cells, unit, half, acc);
-            dst = reinterpret_cast<float4*>(hv + unit * kSB + 8 * half);
-            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            if (want_value) {
+                dense8(w.v_w1t, kH, w.v_b1, xv, cells, unit, half, acc);
+                dst = reinterpret_cast<float4*>(hv + unit * kSB + 8 * half);
+                dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
         }
         __syncthreads();
         // 3. LayerNorm(128) + ReLU per sample
 #pragma unroll
         for (int rep = 0; rep < 2; ++rep) {
             layernorm_relu<kH / 32, false>(nullptr, true, hp, warp + 8 * rep, kH, w.p_ln2_w, w.p_ln2_b, lane);
-            layernorm_relu<kH / 32, false>(nullptr, true, hv, warp + 8 * rep, kH, w.v_ln2_w, w.v_ln2_b, lane);
+            if (want_value) layernorm_relu<kH / 32, false>(nullptr, true, hv, warp + 8 * rep, kH, w.v_ln2_w, w.v_ln2_b, lane);
         }
         __syncthreads();
         // 4. output layers: logits (thread = (cell, 8 samples)), value (warp = 2 samples)
@@ -213,7 +217,7 @@ heads_kernel(const float* __restrict__ pf, const float* __restrict__ vf, long lo
             }
         }
 #pragma unroll
-        for (int rep = 0; rep < 2; ++rep) {
+        for (int rep = 0; rep < 2 && want_value; ++rep) {
             const int sidx = warp + 8 * rep;
             float dot = 0.f;
             for (int k = lane; k < kH; k += 32) dot = fmaf(hv[k * kSB + sidx], __ldg(w.v_w2 + k), dot);
@@ -228,7 +232,7 @@ heads_kernel(const float* __restrict__ pf, const float* __restrict__ vf, long lo
 
 extern "C" int mnk_resnet_heads(const float* policy_feat, const float* value_feat, int64_t rows, int32_t cells,
                                 const mnk_heads_weights_t* w, float* logits, float* values, void* stream) {
-    if (!policy_feat || !value_feat || !w || !logits || !values) return MNK_ERR_NULL;
+    if (!policy_feat || !w || !logits || (values && !value_feat)) return MNK_ERR_NULL;
     const float* const* ptrs = reinterpret_cast<const float* const*>(w);
     for (size_t i = 0; i < sizeof(mnk_heads_weights_t) / sizeof(float*); ++i)
         if (ptrs[i] == nullptr) return MNK_ERR_NULL;

@@ -84,16 +84,16 @@ class NativeResNet:
         self._heads = MnkHeadsWeights(*[self._head_tensors[n].data_ptr() for n in MnkHeadsWeights.NAMES])
 
     @torch.no_grad()
-    def tails(self, pf: torch.Tensor, vf: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """logits f32[N, A], value f32[N, 1] from the tower's head features."""
+    def tails(self, pf: torch.Tensor, vf: torch.Tensor, want_value: bool = True):
+        """logits f32[N, A], value f32[N, 1] (None when `want_value` is False) from the tower's head features."""
         if self.torch_heads:
-            return self.policy_tail(pf), self.value_tail(vf)
+            return self.policy_tail(pf), (self.value_tail(vf) if want_value else None)
         rows, cells = vf.shape
         logits = torch.empty((rows, cells), dtype=torch.float32, device=self._dev)
-        values = torch.empty((rows, 1), dtype=torch.float32, device=self._dev)
+        values = torch.empty((rows, 1), dtype=torch.float32, device=self._dev) if want_value else None
         with torch.cuda.device(self._dev):
             check(self._L.mnk_resnet_heads(pf.data_ptr(), vf.data_ptr(), rows, cells, ctypes.byref(self._heads),
-                                            logits.data_ptr(), values.data_ptr(),
+                                            logits.data_ptr(), values.data_ptr() if want_value else None,
                                             torch.cuda.current_stream(self._dev).cuda_stream), "mnk_resnet_heads")
         return logits, values
 
@@ -110,15 +110,16 @@ class NativeResNet:
         return pf, vf
 
     @torch.no_grad()
-    def forward_env(self, env, swap: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    def forward_env(self, env, swap: Optional[torch.Tensor] = None, want_value: bool = True):
         """Raw policy logits f32[N, m*n] and value f32[N, 1] for the CURRENT state of `env`, read from its
-        bitboards; `swap` u8[N] != 0 exchanges the planes (the canonical view of a white mover/agent)."""
+        bitboards; `swap` u8[N] != 0 exchanges the planes (the canonical view of a white mover/agent).
+        `want_value=False` skips the value head (value is None)."""
         env._fold_mirrors()
         pf, vf = self.features(env._st, env.num_envs, env.m * env.n, swap)
-        return self.tails(pf, vf)
+        return self.tails(pf, vf, want_value)
 
     @torch.no_grad()
-    def forward(self, obs: torch.Tensor, action_mask: Optional[torch.Tensor] = None):
+    def forward(self, obs: torch.Tensor, action_mask: Optional[torch.Tensor] = None, want_value: bool = True):
         """Module-compatible forward(obs f32[B,2,m,n], mask) -> (MaskedCategorical, value[B,1]): the
         observation is packed to bitboards first (mnk_pack_boards), then the same kernel runs."""
         if obs.dim() == 3:
@@ -133,7 +134,7 @@ class NativeResNet:
             check(self._L.mnk_pack_boards(ctypes.byref(st), obs.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream),
                   "mnk_pack_boards")
         pf, vf = self.features(st, b, m * n, None)
-        logits, value = self.tails(pf, vf)
+        logits, value = self.tails(pf, vf, want_value)
         if action_mask is not None and action_mask.dim() == 1:
             action_mask = action_mask.unsqueeze(0)
         return MaskedCategorical(logits, action_mask), value
@@ -160,12 +161,12 @@ class NativeNNPolicy(Policy):
         """Action for the side to move of every env, straight from the bitboards (the wrapper's dense
         opponent call): canonical view = planes swapped where the mover is white."""
         swap = (env._meta & 1).to(torch.uint8)
-        logits, _ = self.net.forward_env(env, swap)
+        logits, _ = self.net.forward_env(env, swap, want_value=False)
         return masked_sample(logits, env.legal_mask(), seed=self.seed, counter=counter, row_offset=env.env_offset,
                              deterministic=deterministic, want_log_prob=False, counter_base=self.counter_base)[0]
 
     def act(self, obs, deterministic: bool = False) -> torch.Tensor:
-        dist, _ = self.net.forward(obs["observation"], obs["action_mask"])
+        dist, _ = self.net.forward(obs["observation"], obs["action_mask"], want_value=False)
         self._calls += 1
         return masked_sample(dist._raw, dist._mask, seed=self.seed, counter=self._calls, deterministic=deterministic,
                              want_log_prob=False, counter_base=self.counter_base)[0]

@@ -138,7 +138,7 @@ def test_native_rollout_matches_generic_rollout_path():
     assert a[6].episodes == b[6].episodes > 0 and a[6].wins == b[6].wins
 
 
-@pytest.mark.parametrize("m,n", [(9, 9), (13, 13), (19, 19), (5, 7)], ids=lambda v: str(v))
+@pytest.mark.parametrize("m,n", [(9, 9), (13, 13), (15, 15), (19, 19), (5, 7), (20, 20)], ids=lambda v: str(v))
 def test_fused_heads_match_torch_modules(m, n):
     """mnk_resnet_heads (LN -> ReLU -> Linear -> LN -> ReLU -> Linear [-> Tanh], fp32) against the same torch
     modules on the same tower features, including a row count that is not a multiple of the 8-sample batch."""
@@ -164,6 +164,8 @@ def test_fused_heads_match_torch_modules(m, n):
         assert logits.shape == want_l.shape and values.shape == want_v.shape
         assert torch.allclose(logits, want_l, rtol=1e-4, atol=2e-4), (logits - want_l).abs().max()
         assert torch.allclose(values, want_v, rtol=1e-4, atol=1e-5), (values - want_v).abs().max()
+        only_l, none_v = native.tails(pf, vf, want_value=False)        # policy-only (values = NULL in the C ABI)
+        assert none_v is None and torch.equal(only_l, logits)
 
 
 @pytest.mark.parametrize("opponent_kind", ["native_nn", "random"])
