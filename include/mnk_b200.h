@@ -222,7 +222,7 @@ int mnk_episode_stats(const float* rewards, const uint8_t* dones, int64_t num_en
  * implicit-GEMM kernel reading the packed bitboards (swap[e] != 0 exchanges the planes: the mover's /
  * agent's canonical view, as in mnk_observe).  bf16 operands, fp32 accumulation in TMEM.
  *   weights  bf16 [1+2*blocks][9 taps][4 k-chunks][32 c_out][8 c_in]  (tap = ky*3+kx; 16-byte aligned)
- *   bias     f32  [1+2*blocks][32]            head_w f32 [3][32], head_b f32 [3] (policy0, policy1, value)
+ *   bias     f32  [1+2*blocks][32] (16-byte aligned)   head_w f32 [3][32], head_b f32 [3] (policy0, policy1, value)
  *   policy_feat f32 [num_envs][2*m*n]  (= Flatten(Conv2d(32,2,1)(features))), value_feat f32 [num_envs][m*n]
  *   error    NULL or int32[1], set to 1 if an internal barrier wait timed out (results invalid) */
 int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, const void* weights, const float* bias,

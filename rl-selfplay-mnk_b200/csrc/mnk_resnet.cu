@@ -46,7 +46,6 @@ constexpr int kGroups = kBlocksM / kGroupBlocks;
 constexpr int kMmaWarp = 8;                   // warps 0-7 epilogue (lane quarter = warp&3, channel half = warp>>2)
 constexpr int kThreads = 32 * (kMmaWarp + 1); // warp 8: MMA issue + TMA
 constexpr int kTmemCols = 32 * kBlocksM;      // 256
-constexpr int kMaxLayers = 1 + 2 * 8;
 #ifndef MNK_POLL_BACKOFF_NS
 #define MNK_POLL_BACKOFF_NS 96
 #endif
@@ -55,7 +54,6 @@ constexpr unsigned kPollBackoffNs = MNK_POLL_BACKOFF_NS;
 struct Smem {
     alignas(128) unsigned char act[2][kActBytes];
     alignas(128) unsigned char wts[2][kLayerWeightBytes];
-    alignas(16) float bias[kMaxLayers][kC];
     alignas(16) float head_w[3][kC];
     float head_b[4];
     alignas(8) unsigned long long mma_bar[kBlocksM];
@@ -79,10 +77,24 @@ MNK_DEV void mbar_expect_tx(void* bar, u32 bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // bounded wait: returns false instead of hanging if the phase never completes
+#ifndef MNK_WAIT_HINT_NS
+#define MNK_WAIT_HINT_NS 0
+#endif
 MNK_DEV bool mbar_wait(void* bar, u32 parity) {
     const u32 addr = smem_u32(bar);
     for (int spin = 0; spin < (1 << 18); ++spin) {
         u32 done;
+#if MNK_WAIT_HINT_NS > 0
+        // hardware-suspended wait: the thread sleeps inside try_wait until the phase completes or the hint expires
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity), "r"((u32)MNK_WAIT_HINT_NS)
+            : "memory");
+        if (done) return true;
+#else
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -94,6 +106,7 @@ MNK_DEV bool mbar_wait(void* bar, u32 parity) {
         // back off: a spinning try_wait is a shared-memory access per poll, and 8 polling warps took ~a quarter
         // of the shared-memory pipe away from the tensor core's operand reads (ncu, profiles/README.md)
         __nanosleep(kPollBackoffNs);
+#endif
     }
     return false;
 }
@@ -116,6 +129,18 @@ MNK_DEV void umma_bf16(u32 tmem_d, u64 desc_a, u64 desc_b, u32 accumulate) {
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate)
+        : "memory");
+}
+// same, descriptors given as (low word, high word): the high words are layer constants and the low words
+// (14-bit start address fields) advance by plain 32-bit adds in the issue loop
+MNK_DEV void umma_bf16_lohi(u32 tmem_d, u32 a_lo, u32 a_hi, u32 b_lo, u32 b_hi, u32 accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(kIdesc), "r"(accumulate)
         : "memory");
 }
 MNK_DEV void umma_commit(void* bar) {
@@ -160,6 +185,30 @@ MNK_DEV void tmem_ld16(u32 taddr, u32 (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// split form: issue the load, do other work, then wait (the wait names the registers so that no use is hoisted above it)
+MNK_DEV void tmem_ld16_issue(u32 taddr, u32 (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+MNK_DEV void tmem_ld_wait(u32 (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
+
+#ifndef MNK_EPI_PIPE
+#define MNK_EPI_PIPE 1
+#endif
+#ifndef MNK_EPI_PACKSEL
+#define MNK_EPI_PACKSEL 1
+#endif
+
 // bias (+ skip) + ReLU + bf16 store of NCH channels [ch0, ch0+NCH) of pixel row i; returns the fp32 values
 template <int NCH>
 MNK_DEV void epilogue_row(Smem& sm, const u32* acc, const float (&bias)[NCH], int out_buf, int i, int ch0, bool skip, bool valid,
@@ -183,8 +232,16 @@ MNK_DEV void epilogue_row(Smem& sm, const u32* acc, const float (&bias)[NCH], in
             }
         }
     }
+#if MNK_EPI_PACKSEL
+    // guard rows are zeroed on the packed words (8 selects instead of 16); v[] of a guard row is not used by callers
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) v[ch] = fmaxf(v[ch], 0.0f);
+    const u32 keep = valid ? 0xFFFFFFFFu : 0u;
+#else
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) v[ch] = valid ? fmaxf(v[ch], 0.0f) : 0.0f;
+    const u32 keep = 0xFFFFFFFFu;
+#endif
     if (store) {
 #pragma unroll
         for (int kc = 0; kc < NKC; ++kc) {
@@ -192,7 +249,7 @@ MNK_DEV void epilogue_row(Smem& sm, const u32* acc, const float (&bias)[NCH], in
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
                 const __nv_bfloat162 pr = __floats2bfloat162_rn(v[kc * 8 + 2 * h], v[kc * 8 + 2 * h + 1]);
-                w[h] = *reinterpret_cast<const u32*>(&pr);
+                w[h] = *reinterpret_cast<const u32*>(&pr) & keep;
             }
             *out_row[kc] = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -214,15 +271,24 @@ __global__ void __launch_bounds__(kThreads, 2) resnet_tower_kernel(Params p) {
         mbar_init(&sm.wts_bar[0], 1);
         mbar_init(&sm.wts_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // first layer's weights: in flight while the tile is zeroed and the boards are decoded
+        mbar_expect_tx(&sm.wts_bar[0], kLayerWeightBytes);
+        tma_bulk_g2s(&sm.wts[0][0], p.weights, kLayerWeightBytes, &sm.wts_bar[0]);
     }
     if (warp == kMmaWarp) {   // TMEM allocation is a warp-wide operation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    {   // zero both activation buffers, load biases / head weights
-        uint4* z = reinterpret_cast<uint4*>(&sm.act[0][0]);
-        for (int i = tid; i < 2 * kActBytes / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
-        for (int i = tid; i < p.layers * kC; i += kThreads) (&sm.bias[0][0])[i] = p.bias[i];
+    {   // Zero what no epilogue will write before it is read: k-chunks 0-1 of buffer 0 (the input layer reads
+        // them; the decode below sets the stones) and the margins of every other k-chunk -- each epilogue
+        // rewrites all kRows rows of its output buffer, zeros included.  Then the head weights.
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        uint4* a0 = reinterpret_cast<uint4*>(&sm.act[0][0]);
+        for (int i = tid; i < 2 * kBufRows; i += kThreads) a0[i] = zero;
+        for (int i = tid; i < 6 * 2 * kMargin; i += kThreads) {      // 6 remaining (buffer, k-chunk) planes x 2 margins
+            const int plane = 2 + i / (2 * kMargin), r = i % (2 * kMargin);
+            a0[plane * kBufRows + (r < kMargin ? r : kRows + r)] = zero;
+        }
         for (int i = tid; i < 3 * kC; i += kThreads) (&sm.head_w[0][0])[i] = p.head_w[i];
         if (tid < 3) sm.head_b[tid] = p.head_b[tid];
     }
@@ -257,10 +323,22 @@ __global__ void __launch_bounds__(kThreads, 2) resnet_tower_kernel(Params p) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const u32 tmem_base = sm.tmem_base;
     bool ok = true;
+#ifdef MNK_TIMELINE   // debug build only (tools/timeline_tower.py): per-layer cycle stamps of one mid-grid CTA into error[1..]
+    const long long t_origin = clock64();
+    const bool stamp = p.error != nullptr && blockIdx.x == gridDim.x / 2 && lane == 0;
+#define MNK_STAMP(slot) do { if (stamp) p.error[1 + 8 * L + (slot)] = (int)(clock64() - t_origin); } while (0)
+#else
+#define MNK_STAMP(slot) do { } while (0)
+#endif
 
-    if (warp == kMmaWarp && elect_one()) {   // first layer's weights
-        mbar_expect_tx(&sm.wts_bar[0], kLayerWeightBytes);
-        tma_bulk_g2s(&sm.wts[0][0], p.weights, kLayerWeightBytes, &sm.wts_bar[0]);
+    int tap_rows[kTaps];   // row shift of each 3x3 tap in the guard-strided tile
+#pragma unroll
+    for (int tap = 0; tap < kTaps; ++tap) {
+#ifdef MNK_EXP_TAP_OFF   // timing experiments only (wrong results)
+        tap_rows[tap] = MNK_EXP_TAP_OFF;
+#else
+        tap_rows[tap] = (tap / 3 - 1) * p.pw + (tap % 3 - 1);
+#endif
     }
 
     for (int L = 0; L < p.layers; ++L) {
@@ -272,45 +350,76 @@ __global__ void __launch_bounds__(kThreads, 2) resnet_tower_kernel(Params p) {
             // tcgen05 / TMA instruction: with a divergent `if (lane == 0)` region the compiler cannot
             // prove the descriptors uniform and wraps every MMA in an ELECT/R2UR waterfall loop
             // (~100 cycles per MMA on the issuing thread; ncu source page, profiles/).
-            if (L + 1 < p.layers && elect_one()) {   // prefetch next layer's weights into the other ring slot
+            // next layer's weights into the other ring slot, ahead of this layer's MMAs (issuing the copy from inside
+            // the MMA loop instead was 6 % slower: timeline in profiles/README.md)
+            if (L + 1 < p.layers && elect_one()) {
                 mbar_expect_tx(&sm.wts_bar[(L + 1) & 1], kLayerWeightBytes);
                 tma_bulk_g2s(&sm.wts[(L + 1) & 1][0], p.weights + (size_t)(L + 1) * kLayerWeightBytes, kLayerWeightBytes,
                              &sm.wts_bar[(L + 1) & 1]);
             }
             ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.wts_bar[L & 1], (L >> 1) & 1)) != 0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const u32 a_base = smem_u32(&sm.act[in_buf][0]);
-            const u32 w_base = smem_u32(&sm.wts[L & 1][0]);
-            const int ksteps = (L == 0) ? 1 : kC / 16;   // the input layer has 2 real channels: one K=16 step
-            // Back-to-back MMAs into ONE accumulator serialise on the accumulate latency; interleaving
-            // the kGroupBlocks M-blocks of a group gives independent chains.
-            for (int g = 0; g < kGroups; ++g) {
-                u32 acc = 0;
-                for (int tap = 0; tap < kTaps; ++tap) {
-                    const int off = (tap / 3 - 1) * p.pw + (tap % 3 - 1);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const u64 b_desc = umma_desc(w_base + (u32)((tap * kChunks + 2 * ks) * kC) * 16, kC * 16, 128);
-                        const u32 a_addr0 = a_base + (u32)(2 * ks) * (kBufRows * 16) + (u32)(kMargin + 128 * g * kGroupBlocks + off) * 16;
-                        const u64 a_desc0 = umma_desc(a_addr0, kBufRows * 16, 128);
-                        if (elect_one()) {
+            MNK_STAMP(0);   // MMA warp: issue loop starts
+            // Descriptor words: the start-address field is (shared address >> 4); every tap / k-step / M-block
+            // is that field plus a constant, so the fully unrolled loop below spends one add per operand.  (With
+            // the index arithmetic in the loop the issuing thread needed ~60 cycles per MMA -- more than the 40
+            // the tensor core takes to read the operands -- and the loop, not the pipe, set the pace: timeline
+            // in profiles/README.md.)
+            static_assert(kGroups == 1, "one interleaved group of M-blocks per layer");
+            const u64 a_d0 = umma_desc(smem_u32(&sm.act[in_buf][0]) + kMargin * 16, kBufRows * 16, 128);   // row 0 of the tile, k-chunk 0
+            const u64 b_d0 = umma_desc(smem_u32(&sm.wts[L & 1][0]), kC * 16, 128);
+            const u32 a_lo0 = (u32)a_d0, a_hi = (u32)(a_d0 >> 32);      // low word: start-address field (bits 0-13) + LBO (bits 16-29)
+            const u32 b_lo0 = (u32)b_d0, b_hi = (u32)(b_d0 >> 32);
+            const bool two_ksteps = (L != 0);   // the input layer has 2 real channels: one K=16 step
 #pragma unroll
-                            for (int jj = 0; jj < kGroupBlocks; ++jj)   // next M-block: +128 rows = +2048 B = +128 in the address field
-                                umma_bf16(tmem_base + 32 * (g * kGroupBlocks + jj), a_desc0 + (u64)(128 * jj), b_desc, acc);
+            for (int tap = 0; tap < kTaps; ++tap) {
+                const u32 a_tap = a_lo0 + (u32)tap_rows[tap];                 // rows are 16 B: row offset == field offset
+                const u32 b_tap = b_lo0 + (u32)(tap * kChunks * kC);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        if (ks == 0 || two_ksteps) {
+#pragma unroll
+                            for (int jj = 0; jj < kBlocksM; ++jj)   // next M-block: +128 rows
+                                umma_bf16_lohi(tmem_base + 32 * jj, a_tap + (u32)(2 * ks * kBufRows + 128 * jj), a_hi,
+                                               b_tap + (u32)(2 * ks * kC), b_hi, (tap | ks) != 0);
                         }
-                        __syncwarp();
-                        acc = 1;
                     }
                 }
-                if (elect_one()) umma_commit(&sm.mma_bar[g]);
                 __syncwarp();
             }
+            if (elect_one()) umma_commit(&sm.mma_bar[0]);
+            __syncwarp();
+            MNK_STAMP(1);   // MMA warp: all MMAs of the layer issued and committed
         } else {
-            float bias[16];   // this warp's 16 channels of the layer's folded bias: 4 vector loads per layer, not 16 scalar loads per block
+            // this warp's 16 channels of the layer's folded bias, straight from global memory (L1-resident, issued
+            // before the wait on the MMAs): as shared-memory loads they cost 2 % of the pipe the tensor core reads through
+            float bias[16];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
-                const float4 b4 = reinterpret_cast<const float4*>(&sm.bias[L][16 * half])[q4];
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + L * kC + 16 * half) + q4);
                 bias[4 * q4] = b4.x; bias[4 * q4 + 1] = b4.y; bias[4 * q4 + 2] = b4.z; bias[4 * q4 + 3] = b4.w;
             }
+#if MNK_EPI_PIPE
+            if (!last) {   // kGroups == 1: one wait, then the TMEM load of block j+1 is in flight under the arithmetic of block j
+                static_assert(kGroups == 1, "pipelined epilogue assumes one commit per layer");
+                ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[0], L & 1)) != 0;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (warp == 0) MNK_STAMP(2);   // epilogue warp 0: MMAs complete (woken)
+                const u32 t0 = tmem_base + ((u32)(quarter * 32) << 16) + 16 * half;
+                u32 acc[2][16];
+                tmem_ld16_issue(t0, acc[0]);
+#pragma unroll
+                for (int j = 0; j < kBlocksM; ++j) {
+                    tmem_ld_wait(acc[j & 1]);
+                    if (j + 1 < kBlocksM) tmem_ld16_issue(t0 + 32 * (j + 1), acc[(j + 1) & 1]);
+                    float v[16];
+                    epilogue_row<16>(sm, acc[j & 1], bias, out_buf, 128 * j + quarter * 32 + lane, 16 * half, skip,
+                                     (valid_bits >> j) & 1u, true, v);
+                }
+                if (warp == 0) MNK_STAMP(3);   // epilogue warp 0: its four blocks done
+            } else
+#endif
             for (int j = 0; j < kBlocksM; ++j) {
                 if (j % kGroupBlocks == 0) {
                     ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[j / kGroupBlocks], L & 1)) != 0;   // warp-uniform
@@ -359,6 +468,7 @@ __global__ void __launch_bounds__(kThreads, 2) resnet_tower_kernel(Params p) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp == kMmaWarp) MNK_STAMP(4);   // layer barrier passed
     }
     if (!ok && p.error != nullptr) atomicExch(p.error, 1);
     if (warp == kMmaWarp) {
@@ -373,7 +483,7 @@ extern "C" int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, cons
     if (int rc = mnk_check_state(st)) return rc;
     if (!weights || !bias || !head_w || !head_b || !policy_feat || !value_feat) return MNK_ERR_NULL;
     if (blocks < 1 || blocks > 8) return MNK_ERR_ARG;
-    if (reinterpret_cast<uintptr_t>(weights) & 15u) return MNK_ERR_ALIGN;
+    if ((reinterpret_cast<uintptr_t>(weights) | reinterpret_cast<uintptr_t>(bias)) & 15u) return MNK_ERR_ALIGN;
     if (st->num_envs == 0) return MNK_OK;
     rn::Params p;
     p.m = st->m; p.n = st->n; p.words = st->words; p.layers = 1 + 2 * blocks;
@@ -385,7 +495,10 @@ extern "C" int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, cons
     p.bits = reinterpret_cast<const u64*>(st->bits);
     p.swap = swap; p.weights = static_cast<const unsigned char*>(weights); p.bias = bias;
     p.head_w = head_w; p.head_b = head_b; p.policy_feat = policy_feat; p.value_feat = value_feat; p.error = error;
-    const size_t smem = sizeof(rn::Smem) + 128;
+#ifndef MNK_EXTRA_SMEM   // experiments only: pad the request to force one CTA per SM
+#define MNK_EXTRA_SMEM 0
+#endif
+    const size_t smem = sizeof(rn::Smem) + 128 + MNK_EXTRA_SMEM;
     static std::atomic<size_t> granted[kMaxDevices];
     if (int rc = mnk_optin_smem(rn::resnet_tower_kernel, smem, granted)) return rc;
     const unsigned grid = (unsigned)((st->num_envs + p.spc - 1) / p.spc);

@@ -3,7 +3,9 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "rl-selfplay-mnk_b200")); sys.path.insert(0, ROOT)
 import torch
-from mnk_b200 import NativeResNet, ResNetActorCritic, TorchVectorMnkEnv
+from mnk_b200 import NativeResNet, ResNetActorCritic, TorchVectorMnkEnv, _lib
+if os.environ.get("MNK_LIB"):          # A/B experiments: a variant build of the library (tools/ab_tower.sh)
+    _lib.LIB_PATH = os.path.abspath(os.environ["MNK_LIB"])
 
 m, n, k = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (9, 9, 5)))
 flops_per_sample = {(9, 9): 12.136e6, (13, 13): 25.3e6, (19, 19): 54.1e6}[(m, n)]
@@ -11,7 +13,7 @@ torch.manual_seed(0)
 net = ResNetActorCritic((2, m, n), m * n).cuda().eval()
 native = NativeResNet(net)
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops_sustained": 1391.8}
-for ne in (4096, 32768, 262144):
+for ne in (4096, 32768, 262144)[: int(os.environ.get('MNK_SIZES', 3))]:
     env = TorchVectorMnkEnv(m, n, k, ne, device="cuda")
     env.reset()
     for t in range(20):
@@ -32,6 +34,11 @@ for ne in (4096, 32768, 262144):
     e1.record(); torch.cuda.synchronize()
     ms_full = e0.elapsed_time(e1) / reps
     pf, vf = native.features(env._st, ne, m * n, None)
+    if ne == 4096 and os.environ.get("MNK_SAVE"):
+        torch.save((pf.cpu(), vf.cpu()), os.environ["MNK_SAVE"])
+    if ne == 4096 and os.environ.get("MNK_CHECK"):
+        want_pf, want_vf = torch.load(os.environ["MNK_CHECK"])
+        print("variant vs saved features: max |d| =", float((pf.cpu() - want_pf).abs().max()), float((vf.cpu() - want_vf).abs().max()))
     for _ in range(3):
         native.tails(pf, vf)
     torch.cuda.synchronize()
