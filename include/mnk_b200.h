@@ -229,6 +229,14 @@ int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, const void* wei
                      const float* head_w, const float* head_b, int32_t blocks, float* policy_feat,
                      float* value_feat, int32_t* error, void* stream);
 
+/* The same tower for boards with 3 <= m <= 10 rows (MNK_ERR_GEOM otherwise), with the three vertical taps fused
+ * into the MMA's N dimension (csrc/mnk_resnet_rows.cu): identical arguments and results, except the weight layout
+ *   weights_rows  bf16 [1+2*blocks][3 kx][4 k-chunks][ky*32 + c_out][8 c_in]   (16-byte aligned)
+ * 2.1x fewer shared-memory operand reads per layer; the faster kernel wherever the board fits. */
+int mnk_resnet_tower_rows(const mnk_state_t* st, const uint8_t* swap, const void* weights_rows, const float* bias,
+                          const float* head_w, const float* head_b, int32_t blocks, float* policy_feat,
+                          float* value_feat, int32_t* error, void* stream);
+
 /* The heads' tails after the tower (resnet.py:41-63), one kernel, fp32:
  *   logits = Linear(128,A)(ReLU(LN(128)(Linear(2A,128)(ReLU(LN(2A)(policy_feat))))))
  *   values = Tanh(Linear(128,1)(ReLU(LN(128)(Linear(A,128)(ReLU(LN(A)(value_feat)))))))

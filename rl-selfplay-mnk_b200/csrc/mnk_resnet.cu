@@ -28,6 +28,7 @@
 //   * The input is read straight from the packed bitboards (72 B per env at 9x9) and the last
 //     epilogue applies the two 1x1 head convolutions from fp32 registers and stores the features.
 #include "mnk_dispatch.cuh"
+#include "mnk_umma.cuh"
 
 #include <cuda_bf16.h>
 
@@ -46,10 +47,7 @@ constexpr int kGroups = kBlocksM / kGroupBlocks;
 constexpr int kMmaWarp = 8;                   // warps 0-7 epilogue (lane quarter = warp&3, channel half = warp>>2)
 constexpr int kThreads = 32 * (kMmaWarp + 1); // warp 8: MMA issue + TMA
 constexpr int kTmemCols = 32 * kBlocksM;      // 256
-#ifndef MNK_POLL_BACKOFF_NS
-#define MNK_POLL_BACKOFF_NS 96
-#endif
-constexpr unsigned kPollBackoffNs = MNK_POLL_BACKOFF_NS;
+using namespace mnk_umma;
 
 struct Smem {
     alignas(128) unsigned char act[2][kActBytes];
@@ -62,102 +60,8 @@ struct Smem {
     unsigned int tmem_base;
 };
 
-MNK_DEV u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-
-MNK_DEV bool elect_one() {   // one lane of a converged warp
-    u32 pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
-MNK_DEV void mbar_init(void* bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-MNK_DEV void mbar_expect_tx(void* bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// bounded wait: returns false instead of hanging if the phase never completes
-#ifndef MNK_WAIT_HINT_NS
-#define MNK_WAIT_HINT_NS 0
-#endif
-MNK_DEV bool mbar_wait(void* bar, u32 parity) {
-    const u32 addr = smem_u32(bar);
-    for (int spin = 0; spin < (1 << 18); ++spin) {
-        u32 done;
-#if MNK_WAIT_HINT_NS > 0
-        // hardware-suspended wait: the thread sleeps inside try_wait until the phase completes or the hint expires
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity), "r"((u32)MNK_WAIT_HINT_NS)
-            : "memory");
-        if (done) return true;
-#else
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return true;
-        // back off: a spinning try_wait is a shared-memory access per poll, and 8 polling warps took ~a quarter
-        // of the shared-memory pipe away from the tensor core's operand reads (ncu, profiles/README.md)
-        __nanosleep(kPollBackoffNs);
-#endif
-    }
-    return false;
-}
-MNK_DEV void tma_bulk_g2s(void* dst, const void* src, u32 bytes, void* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor: start address, LBO (distance between the two
-// 16-byte k-chunks of one MMA), SBO (distance between 8-row groups), version = 1 (Blackwell)
-MNK_DEV u64 umma_desc(u32 saddr, u32 lbo_bytes, u32 sbo_bytes) {
-    return (u64)((saddr & 0x3FFFFu) >> 4) | ((u64)(lbo_bytes >> 4) << 16) | ((u64)(sbo_bytes >> 4) << 32) | (1ull << 46);
-}
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = 32
-constexpr u32 kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(kC >> 3) << 17) | ((128u >> 4) << 24);
-
-MNK_DEV void umma_bf16(u32 tmem_d, u64 desc_a, u64 desc_b, u32 accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate)
-        : "memory");
-}
-// same, descriptors given as (low word, high word): the high words are layer constants and the low words
-// (14-bit start address fields) advance by plain 32-bit adds in the issue loop
-MNK_DEV void umma_bf16_lohi(u32 tmem_d, u32 a_lo, u32 a_hi, u32 b_lo, u32 b_hi, u32 accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(kIdesc), "r"(accumulate)
-        : "memory");
-}
-MNK_DEV void umma_commit(void* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-MNK_DEV void tmem_ld32(u32 taddr, u32 (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
+constexpr u32 kIdesc = umma_idesc_bf16(kC);
 
 struct Params {
     int m, n, words, layers;          // layers = 1 + 2*blocks
@@ -174,33 +78,6 @@ struct Params {
     float* value_feat;                // f32 [num_envs][cells]
     int* error;                       // set to 1 on an mbarrier timeout
 };
-
-MNK_DEV void tmem_ld16(u32 taddr, u32 (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// split form: issue the load, do other work, then wait (the wait names the registers so that no use is hoisted above it)
-MNK_DEV void tmem_ld16_issue(u32 taddr, u32 (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-MNK_DEV void tmem_ld_wait(u32 (&v)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
-                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-                 :
-                 : "memory");
-}
 
 #ifndef MNK_EPI_PIPE
 #define MNK_EPI_PIPE 1
@@ -382,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 2) resnet_tower_kernel(Params p) {
 #pragma unroll
                             for (int jj = 0; jj < kBlocksM; ++jj)   // next M-block: +128 rows
                                 umma_bf16_lohi(tmem_base + 32 * jj, a_tap + (u32)(2 * ks * kBufRows + 128 * jj), a_hi,
-                                               b_tap + (u32)(2 * ks * kC), b_hi, (tap | ks) != 0);
+                                               b_tap + (u32)(2 * ks * kC), b_hi, kIdesc, (tap | ks) != 0);
                         }
                     }
                 }

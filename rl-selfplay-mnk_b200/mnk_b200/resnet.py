@@ -39,9 +39,22 @@ def _arrange(w: torch.Tensor) -> torch.Tensor:
     return t.permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)   # [tap][kc][c_out][j]
 
 
+def _arrange_rows(w: torch.Tensor) -> torch.Tensor:
+    """Same parameters for the board-row kernel (mnk_resnet_tower_rows): bf16 [kx][k-chunk=4][ky*32 + c_out][8 c_in]."""
+    c_out, c_in = w.shape[0], w.shape[1]
+    full = torch.zeros((c_out, 32, 3, 3), dtype=torch.float32, device=w.device)
+    full[:, :c_in] = w
+    t = full.permute(3, 1, 2, 0).reshape(3, 4, 8, 3, c_out)        # [kx][kc][j][ky][c_out]
+    return t.permute(0, 1, 3, 4, 2).reshape(3, 4, 3 * c_out, 8).contiguous().to(torch.bfloat16)
+
+
+ROWS_KERNEL_BOARD_ROWS = (3, 10)      # mnk_resnet_tower_rows: boards with 3 <= m <= 10 rows (shared-memory bound)
+
+
 class NativeResNet:
     def __init__(self, model: nn.Module, device="cuda", torch_heads: bool = False):
         self.torch_heads = torch_heads      # run the head tails through the original torch modules (debug / comparison)
+        self.use_rows_kernel = True         # board-row tower kernel where the board fits it (m <= 10); False = tap kernel
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("mnk_b200.NativeResNet: CUDA only (no CPU fallback)")
@@ -63,6 +76,7 @@ class NativeResNet:
         folded = [_fold(c, b) for c, b in convs]
         dev = self._dev
         self.weights = torch.stack([_arrange(w.to(dev)) for w, _ in folded]).contiguous()    # bf16 [L][9][4][32][8]
+        self.weights_rows = torch.stack([_arrange_rows(w.to(dev)) for w, _ in folded]).contiguous()   # bf16 [L][3][4][96][8]
         self.bias = torch.stack([b.to(dev) for _, b in folded]).contiguous()                  # f32 [L][32]
         pc, vc = model.policy_head[0], model.value_head[0]
         self.head_w = torch.cat([pc.weight.reshape(2, 32), vc.weight.reshape(1, 32)]).float().to(dev).contiguous()
@@ -101,12 +115,13 @@ class NativeResNet:
     def features(self, state: MnkState, num_envs: int, cells: int, swap: Optional[torch.Tensor]):
         pf = torch.empty((num_envs, 2 * cells), dtype=torch.float32, device=self._dev)
         vf = torch.empty((num_envs, cells), dtype=torch.float32, device=self._dev)
+        rows = self.use_rows_kernel and ROWS_KERNEL_BOARD_ROWS[0] <= state.m <= ROWS_KERNEL_BOARD_ROWS[1]
+        entry, name, weights = ((self._L.mnk_resnet_tower_rows, "mnk_resnet_tower_rows", self.weights_rows) if rows else
+                                (self._L.mnk_resnet_tower, "mnk_resnet_tower", self.weights))
         with torch.cuda.device(self._dev):
-            check(self._L.mnk_resnet_tower(ctypes.byref(state), None if swap is None else swap.data_ptr(),
-                                            self.weights.data_ptr(), self.bias.data_ptr(), self.head_w.data_ptr(),
-                                            self.head_b.data_ptr(), self.blocks, pf.data_ptr(), vf.data_ptr(),
-                                            self._err.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream),
-                  "mnk_resnet_tower")
+            check(entry(ctypes.byref(state), None if swap is None else swap.data_ptr(), weights.data_ptr(),
+                        self.bias.data_ptr(), self.head_w.data_ptr(), self.head_b.data_ptr(), self.blocks, pf.data_ptr(),
+                        vf.data_ptr(), self._err.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream), name)
         return pf, vf
 
     @torch.no_grad()

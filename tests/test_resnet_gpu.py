@@ -49,6 +49,49 @@ def test_native_forward_matches_reference(path):
     assert (np.argmax(np.where(fin, got, -np.inf), 1) == np.argmax(np.where(fin, want, -np.inf), 1))[clear].all()
 
 
+@pytest.mark.parametrize("m,n,k", [(3, 3, 3), (5, 7, 4), (7, 7, 4), (9, 9, 5), (10, 10, 5), (6, 22, 5), (4, 15, 4)], ids=str)
+def test_board_row_kernel_matches_tap_kernel_and_fp32_tower(m, n, k):
+    """mnk_resnet_tower_rows (vertical taps fused into N = 96, TMEM slot ring, no per-layer barrier) against
+    mnk_resnet_tower (one N = 32 MMA per tap) and the torch fp32 tower on mid-game positions: env counts that
+    leave a partial last CTA, plane swap, lane layouts that fill all 128 lanes (7x7: 16 envs x 8 lanes)."""
+    from mnk_b200 import NativeResNet, ResNetActorCritic, TorchVectorMnkEnv
+    torch.manual_seed(11)
+    net = ResNetActorCritic((2, m, n), m * n).to(DEV).eval()
+    with torch.no_grad():
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.1)
+                mod.running_var.uniform_(0.7, 1.3)
+                mod.weight.uniform_(0.8, 1.2)
+                mod.bias.normal_(0, 0.1)
+    native = NativeResNet(net, device=DEV)
+    per_cta = 128 // (n + 1)
+    for ne in (1, per_cta, per_cta + 1, 5 * per_cta - 1, 1000):
+        env = TorchVectorMnkEnv(m, n, k, ne, device=DEV)
+        env.reset()
+        for t in range(m * n // 2):
+            env.step_autoreset(env.random_legal_actions(5, t), materialise=False)
+        swap = (torch.arange(ne, device=DEV) % 3 == 0).to(torch.uint8)
+        native.use_rows_kernel = True
+        pf_r, vf_r = native.features(env._st, ne, m * n, swap)
+        native.use_rows_kernel = False
+        pf_t, vf_t = native.features(env._st, ne, m * n, swap)
+        native.check_error()
+        obs = env.observe()["observation"]
+        obs = torch.where(swap.bool()[:, None, None, None], obs.flip(1), obs)
+        with torch.no_grad():
+            feat = net.forward_body(obs)
+            want_p = net.policy_head[1](net.policy_head[0](feat))
+            want_v = net.value_head[1](net.value_head[0](feat))
+        for got, tap, want in ((pf_r, pf_t, want_p), (vf_r, vf_t, want_v)):
+            scale = float(want.abs().max()) + 1e-6
+            # both kernels round activations to bf16 between layers; their fp32 accumulation orders differ
+            assert float((got - tap).abs().max()) <= 2e-2 * scale, (ne, float((got - tap).abs().max()), scale)
+            rel = lambda x: float((x - want).norm() / (want.norm() + 1e-12))
+            assert rel(got) <= 2e-2 and rel(got) <= 1.5 * rel(tap) + 1e-3, (ne, rel(got), rel(tap))   # bf16 activations, 9 layers
+            assert float((got - want).abs().max()) <= 5e-2 * scale
+
+
 def test_native_forward_from_env_bitboards_and_batch_tails():
     """forward_env reads the bitboards directly (no f32 observation) and must agree with forward(obs):
     same kernel, different input path; batch sizes that leave a partial last CTA."""
