@@ -40,13 +40,15 @@ constexpr int kPad = 8;                       // zero rows before / after each a
 constexpr int kSlots = 5;                     // TMEM ring: 5 x 96 columns
 constexpr int kTmemCols = 512;
 constexpr int kLead = 4;                      // MMA blocks in flight ahead of the epilogue
+constexpr int kTokenBarrier0 = 8;             // named barriers 8..12: "the blocks step e needs are committed" (id 8 + e % 5)
 constexpr int kStepBarrier0 = 3;              // named barriers 3..7: "epilogue step e done" (id 3 + e % 5); 1, 2: head exchange of a set
 constexpr int kWtsSlots = 3;
 constexpr int kLayerWeightBytes = 3 * kChunks * kN * 16;   // 18,432
 constexpr int kEpiSets = 2;                   // two sets of 8 epilogue warps take alternate steps (the step is latency-bound)
 constexpr int kSetWarps = 8;                  // per set: TMEM lane quarter = warp & 3, channel half = (warp >> 2) & 1
 constexpr int kMmaWarp = kEpiSets * kSetWarps;
-constexpr int kThreads = 32 * (kMmaWarp + 1);
+constexpr int kWatchWarp = kMmaWarp + 1;      // turns MMA commits (mbarriers) into named-barrier tokens for the epilogue sets
+constexpr int kThreads = 32 * (kWatchWarp + 1);
 constexpr u32 kIdesc = umma_idesc_bf16(kN);
 
 struct Smem {
@@ -198,6 +200,17 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
                 MNK_STAMP(g, 1);   // MMA warp: block g issued + committed
             }
         }
+    } else if (warp == kWatchWarp) {
+        // ================= commit watcher: while MMAs run, a shared-memory poll (even of a completed mbarrier) waits ~300
+        // cycles behind the tensor core's operand reads; one warp pays that, in step order, and releases the epilogue
+        // set of each step through a hardware barrier ===========================================================
+        for (int e = 0; e < total_steps; ++e) {
+            const int r = e % m;
+            const int need = (r < m - 1) ? e + 1 : e;            // Q_{r+1} is the last slice row r needs
+            ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[need % kSlots], (u32)(need / kSlots) & 1u)) != 0;
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.arrive %0, %1;" ::"r"(kTokenBarrier0 + e % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");
+        }
     } else {
         // ================= epilogue: one board row (128 lanes x 32 channels) per step, sets alternate steps =========
         const int quarter = warp & 3, half = (warp >> 2) & 1, set = warp / kSetWarps;
@@ -219,8 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
             for (int r = 0; r < m; ++r, ++e) {
                 if ((e % kEpiSets) != set) continue;
                 if ((warp % kSetWarps) == 0) MNK_STAMP(e, 6);   // step begins (before the wait)
-                const int need = (r < m - 1) ? e + 1 : e;        // Q_{r+1} is the last slice this row needs
-                ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[need % kSlots], (u32)(need / kSlots) & 1u)) != 0;
+                asm volatile("bar.sync %0, %1;" ::"r"(kTokenBarrier0 + e % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");   // token from the watcher
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if ((warp % kSetWarps) == 0) MNK_STAMP(e, 2);   // epilogue warp 0: the blocks this step needs are committed
                 // out_r = Q_{r-1}[ky=0] + Q_r[ky=1] + Q_{r+1}[ky=2]; a missing neighbour row re-reads Q_r and is dropped
