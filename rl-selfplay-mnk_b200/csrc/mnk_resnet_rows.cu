@@ -41,10 +41,13 @@ constexpr int kSlots = 5;                     // TMEM ring: 5 x 96 columns
 constexpr int kTmemCols = 512;
 constexpr int kLead = 4;                      // MMA blocks in flight ahead of the epilogue
 constexpr int kTokenBarrier0 = 8;             // named barriers 8..12: "the blocks step e needs are committed" (id 8 + e % 5)
-constexpr int kStepBarrier0 = 3;              // named barriers 3..7: "epilogue step e done" (id 3 + e % 5); 1, 2: head exchange of a set
+constexpr int kStepBarrier0 = 3;              // named barriers 3..7: "epilogue step e done" (id 3 + e % 5); 13-15: head exchange of a set
 constexpr int kWtsSlots = 3;
 constexpr int kLayerWeightBytes = 3 * kChunks * kN * 16;   // 18,432
-constexpr int kEpiSets = 2;                   // two sets of 8 epilogue warps take alternate steps (the step is latency-bound)
+#ifndef MNK_EPI_SETS
+#define MNK_EPI_SETS 2
+#endif
+constexpr int kEpiSets = MNK_EPI_SETS;                   // two sets of 8 epilogue warps take alternate steps (the step is latency-bound)
 constexpr int kSetWarps = 8;                  // per set: TMEM lane quarter = warp & 3, channel half = (warp >> 2) & 1
 constexpr int kMmaWarp = kEpiSets * kSetWarps;
 constexpr int kWatchWarp = kMmaWarp + 1;      // turns MMA commits (mbarriers) into named-barrier tokens for the epilogue sets
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
                     }
                     float* part = sm.head_part[set][pos];
                     if (half == 1) { part[0] = h0; part[1] = h1; part[2] = h2; }
-                    asm volatile("bar.sync %0, 256;" ::"r"(1 + set) : "memory");     // the 8 warps of this set
+                    asm volatile("bar.sync %0, 256;" ::"r"(13 + set) : "memory");    // the 8 warps of this set (ids 13-15)
                     if (half == 0 && valid) {
                         h0 += part[0] + sm.head_b[0];
                         h1 += part[1] + sm.head_b[1];
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
                         p.policy_feat[(size_t)env * 2 * cells + cells + cell] = h1;
                         p.value_feat[(size_t)env * cells + cell] = h2;
                     }
-                    asm volatile("bar.sync %0, 256;" ::"r"(1 + set) : "memory");
+                    asm volatile("bar.sync %0, 256;" ::"r"(13 + set) : "memory");
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
