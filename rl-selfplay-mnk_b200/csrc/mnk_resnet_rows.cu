@@ -53,6 +53,7 @@ constexpr int kMmaWarp = kEpiSets * kSetWarps;
 constexpr int kWatchWarp = kMmaWarp + 1;      // turns MMA commits (mbarriers) into named-barrier tokens for the epilogue sets
 constexpr int kThreads = 32 * (kWatchWarp + 1);
 constexpr u32 kIdesc = umma_idesc_bf16(kN);
+static_assert(kEpiSets <= kMinBoardRows && kEpiSets < kSlots, "a set's consecutive steps lie in the same or the next layer");
 
 struct Smem {
     alignas(128) unsigned char wts[kWtsSlots][kLayerWeightBytes];
@@ -221,28 +222,38 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
         const int s = pos / p.pw, c = pos - s * p.pw;
         const bool valid = s < envs_here && c < p.n;
         const u32 t_lane = tmem_base + ((u32)(quarter * 32) << 16) + (u32)(16 * half);
-        int e = 0;
-        for (int L = 0; L < p.layers; ++L) {
-            const int out_buf = (L & 1) ^ 1;
-            const bool skip = (L >= 2) && ((L & 1) == 0);        // second conv of a residual block adds its block input
-            const bool last = (L == p.layers - 1);
-            float bias[16];
+        // This set's steps are e = set, set + kEpiSets, ...  Layer, board row and the TMEM ring position advance
+        // incrementally (the divisions and the skipped iterations of a plain loop nest were a third of the
+        // instructions this kernel executed: ncu opcode histogram, profiles/README.md).
+        int e = set, L = 0, r = set;                 // kEpiSets <= kMinBoardRows: the first step lies in layer 0
+        int col = (set % kSlots) * kN;              // TMEM column of slot e % kSlots
+        int bar = set % kSlots;                     // e % kSlots: index of this step's named barriers
+        bool new_layer = true, skip = false, last = false;
+        float bias[16];
+        uint4* layer_out = nullptr;
+        while (e < total_steps) {
+            if (new_layer) {
+                const int out_buf = (L & 1) ^ 1;
+                skip = (L >= 2) && ((L & 1) == 0);           // second conv of a residual block adds its block input
+                last = (L == p.layers - 1);
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + L * kC + 16 * half) + q4);
-                bias[4 * q4] = b4.x; bias[4 * q4 + 1] = b4.y; bias[4 * q4 + 2] = b4.z; bias[4 * q4 + 3] = b4.w;
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + L * kC + 16 * half) + q4);
+                    bias[4 * q4] = b4.x; bias[4 * q4 + 1] = b4.y; bias[4 * q4 + 2] = b4.z; bias[4 * q4 + 3] = b4.w;
+                }
+                layer_out = act + (size_t)(out_buf * kChunks + 2 * half) * plane16 + (kPad + pos);
             }
-            for (int r = 0; r < m; ++r, ++e) {
-                if ((e % kEpiSets) != set) continue;
+            {
                 if ((warp % kSetWarps) == 0) MNK_STAMP(e, 6);   // step begins (before the wait)
-                asm volatile("bar.sync %0, %1;" ::"r"(kTokenBarrier0 + e % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");   // token from the watcher
+                asm volatile("bar.sync %0, %1;" ::"r"(kTokenBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");   // token from the watcher
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if ((warp % kSetWarps) == 0) MNK_STAMP(e, 2);   // epilogue warp 0: the blocks this step needs are committed
                 // out_r = Q_{r-1}[ky=0] + Q_r[ky=1] + Q_{r+1}[ky=2]; a missing neighbour row re-reads Q_r and is dropped
                 const bool up = r > 0, down = r < m - 1;
+                const int col_up = up ? (col == 0 ? (kSlots - 1) * kN : col - kN) : col;
+                const int col_down = down ? (col == (kSlots - 1) * kN ? 0 : col + kN) : col;
                 u32 q0[16], q1[16], q2[16];
-                tmem_ld16x3_issue(t_lane + (u32)(((up ? e - 1 : e) % kSlots) * kN), t_lane + (u32)((e % kSlots) * kN + kC),
-                                  t_lane + (u32)(((down ? e + 1 : e) % kSlots) * kN + 2 * kC), q0, q1, q2);
+                tmem_ld16x3_issue(t_lane + (u32)col_up, t_lane + (u32)(col + kC), t_lane + (u32)(col_down + 2 * kC), q0, q1, q2);
                 tmem_ld_wait(q0);
                 tmem_ld_wait(q1);
                 tmem_ld_wait(q2);
@@ -256,9 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
                     v[ch] = a;
                 }
                 uint4* out_row[2];
-#pragma unroll
-                for (int kc = 0; kc < 2; ++kc)
-                    out_row[kc] = act + (size_t)(out_buf * kChunks + 2 * half + kc) * plane16 + (kPad + r * 128 + pos);
+                out_row[0] = layer_out + r * 128;
+                out_row[1] = out_row[0] + plane16;
                 if (skip) {
 #pragma unroll
                     for (int kc = 0; kc < 2; ++kc) {
@@ -312,11 +322,18 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
                     asm volatile("bar.sync %0, 256;" ::"r"(13 + set) : "memory");
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-if (e + lead < total_steps)   // the last `lead` steps have no consumer
-                    asm volatile("bar.arrive %0, %1;" ::"r"(kStepBarrier0 + e % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");
+                if (e + lead < total_steps)   // the last `lead` steps have no consumer
+                    asm volatile("bar.arrive %0, %1;" ::"r"(kStepBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
                 if ((warp % kSetWarps) == 0) MNK_STAMP(e, 4);   // step done
             }
+            e += kEpiSets;
+            r += kEpiSets;
+            new_layer = r >= m;
+            if (new_layer) { r -= m; ++L; }
+            col += kEpiSets * kN;
+            if (col >= kSlots * kN) col -= kSlots * kN;
+            bar += kEpiSets;
+            if (bar >= kSlots) bar -= kSlots;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
