@@ -20,7 +20,14 @@
 //     the epilogue, and because block b of layer L+1 needs only ROW b of layer L's output, the pipeline rolls
 //     across layer boundaries: there is no per-layer barrier.  MMA block g waits for epilogue step g-4 (its TMEM
 //     slot is free and, steps completing in order, its input row is written); epilogue step e waits for the
-//     commit of MMA block e+1 (Q_{r+1}).  Per-layer weights stream through a three-slot TMA ring.
+//     commit of MMA block e+1 (Q_{r+1}).  Per-layer weights stream through a three-slot TMA ring;
+//   * hand-overs avoid shared memory.  While MMAs execute, the tensor core's operand reads own the shared-memory
+//     pipe: a poll of a flag or of an mbarrier -- even a completed one -- returns ~300 cycles late (measured with
+//     the -DMNK_TIMELINE build, profiles/README.md).  So "step e done" is a hardware named barrier (the 8 warps of
+//     the step's epilogue set bar.arrive, the MMA warp bar.sync), and a commit-watcher warp waits on the MMA
+//     mbarriers in step order and releases each step's epilogue set through another named barrier;
+//   * 18 warps: two sets of 8 epilogue warps (TMEM lane quarter x channel half) take alternate steps, the MMA /
+//     TMA warp, the watcher.  One CTA per SM (205 KB of shared memory at 9x9, all 512 TMEM columns).
 //
 // Weight layout for this kernel: bf16 [layer][kx 3][k-chunk 4][ky*32 + c_out][8 c_in] (mnk_b200/resnet.py
 // arranges both layouts from the same folded parameters).
