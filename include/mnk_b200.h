@@ -54,6 +54,8 @@ extern "C" {
 #define MNK_STEP_ZEROCOPY 4u    /* mnk_step_host only: host_actions / host_rd are pinned, device-mapped */
                                 /* (UVA) buffers; the kernel reads / writes them over PCIe itself,   */
                                 /* no staging copies (dev_actions / dev_rd may be NULL)              */
+#define MNK_STEP_NOSYNC 16u     /* mnk_step_host only: enqueue, do not synchronise -- the caller waits on the */
+                                /* stream before reading host_rd (lets a host loop double-buffer two env groups) */
 
 typedef struct mnk_state {
     int32_t m, n, k;
@@ -108,7 +110,8 @@ int mnk_step(const mnk_state_t* st, const void* actions, const int64_t* idx, int
  * dev_actions i64|i32[num_envs], dev_rd = 5 * num_envs bytes (f32 rewards then u8 dones);
  * host_rd receives the same 5 * num_envs bytes.  obs / mask stay on the device (may be NULL).
  * With MNK_STEP_ZEROCOPY the step kernel dereferences the pinned host buffers directly (one launch +
- * one synchronise instead of copy + launch + copy + synchronise). */
+ * one synchronise instead of copy + launch + copy + synchronise).  MNK_STEP_NOSYNC leaves the final
+ * synchronise to the caller. */
 int mnk_step_host(const mnk_state_t* st, const void* host_actions, void* dev_actions, void* dev_rd,
                   void* host_rd, float* obs, uint8_t* mask, uint32_t flags, void* stream);
 

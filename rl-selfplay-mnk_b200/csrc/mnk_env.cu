@@ -343,8 +343,8 @@ int mnk_step_host(const mnk_state_t* st, const void* host_actions, void* dev_act
         float* rewards_h = static_cast<float*>(host_rd);
         uint8_t* dones_h = static_cast<uint8_t*>(host_rd) + 4 * n;
         const int rc = mnk_step(st, host_actions, nullptr, st->num_envs, rewards_h, dones_h, obs, mask, nullptr,
-                                flags & ~MNK_STEP_ZEROCOPY, stream);
-        if (rc != MNK_OK) return rc;
+                                flags & ~(MNK_STEP_ZEROCOPY | MNK_STEP_NOSYNC), stream);
+        if (rc != MNK_OK || (flags & MNK_STEP_NOSYNC)) return rc;
         const cudaError_t e = cudaStreamSynchronize(s);
         return e == cudaSuccess ? MNK_OK : (int)e;
     }
@@ -354,10 +354,10 @@ int mnk_step_host(const mnk_state_t* st, const void* host_actions, void* dev_act
     if (e != cudaSuccess) return (int)e;
     float* rewards = static_cast<float*>(dev_rd);
     uint8_t* dones = static_cast<uint8_t*>(dev_rd) + 4 * n;
-    const int rc = mnk_step(st, dev_actions, nullptr, st->num_envs, rewards, dones, obs, mask, nullptr, flags, stream);
+    const int rc = mnk_step(st, dev_actions, nullptr, st->num_envs, rewards, dones, obs, mask, nullptr, flags & ~MNK_STEP_NOSYNC, stream);
     if (rc != MNK_OK) return rc;
     e = cudaMemcpyAsync(host_rd, dev_rd, 5 * n, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess && !(flags & MNK_STEP_NOSYNC)) e = cudaStreamSynchronize(s);
     return e == cudaSuccess ? MNK_OK : (int)e;
 }
 

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 ]
 
 MNK_OK, MNK_ERR_NULL, MNK_ERR_GEOM, MNK_ERR_ALIGN, MNK_ERR_ARG = 0, -1, -2, -3, -4
-STEP_ACTIONS_I32, STEP_AUTORESET, STEP_ZEROCOPY, STEP_PDL = 1, 2, 4, 8
+STEP_ACTIONS_I32, STEP_AUTORESET, STEP_ZEROCOPY, STEP_PDL, STEP_NOSYNC = 1, 2, 4, 8, 16
 
 
 class MnkState(ctypes.Structure):

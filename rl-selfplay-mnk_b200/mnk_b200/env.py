@@ -240,12 +240,14 @@ class TorchVectorMnkEnv:
         return out
 
     def step_host(self, host_actions: torch.Tensor, host_out: torch.Tensor, autoreset: bool = False,
-                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, zero_copy: bool = False):
+                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, zero_copy: bool = False, sync: bool = True):
         """End-to-end step for callers holding HOST buffers: pinned int64 actions in, pinned
         rewards/dones bytes out (5*N bytes: f32 rewards then u8 dones), one H2D + launch + D2H +
         stream sync inside libmnk_b200 (mnk_step_host).  Observation / mask stay on the device.
         zero_copy=True: both host buffers must be pinned (torch .pin_memory()); the kernel then reads the
-        actions and writes rewards / dones over PCIe itself -- one launch + one sync, no staging copies."""
+        actions and writes rewards / dones over PCIe itself -- one launch + one sync, no staging copies.
+        sync=False enqueues without waiting: synchronise the stream the call ran on before reading the returned
+        host views (a host loop can keep two env groups in flight on two streams)."""
         self._fold_mirrors()
         n = self.num_envs
         flags = _lib.STEP_AUTORESET if autoreset else 0
@@ -261,6 +263,8 @@ class TorchVectorMnkEnv:
             dev_actions, dev_rd = self._dev_actions.data_ptr(), self._dev_rd.data_ptr()
         if host_actions.dtype == torch.int32:
             flags |= _lib.STEP_ACTIONS_I32
+        if not sync:
+            flags |= _lib.STEP_NOSYNC
         obs, mask = out if out is not None else self._new_obs()
         self._call(self._L.mnk_step_host, host_actions.data_ptr(), dev_actions, dev_rd, host_out.data_ptr(), _ptr(obs),
                    _ptr(mask), flags)

@@ -225,6 +225,46 @@ def test_host_step_path():
     assert env.state_checksum() == twin.state_checksum()
 
 
+def test_host_step_two_groups_in_flight():
+    """step_host(sync=False): two env groups on two streams, each synchronised only before its results are read;
+    with env_offset the two halves reproduce one env of twice the size step for step."""
+    half, steps = 640, 25
+    whole = make_env(9, 9, 5, 2 * half)
+    whole.reset()
+    groups = [make_env(9, 9, 5, half, env_offset=g * half) for g in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    host_a = [torch.empty((steps, half), dtype=torch.long).pin_memory() for _ in range(2)]
+    host_out = [[torch.empty(5 * half, dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(2)]
+    want = []
+    for t in range(steps):                        # the action trace and the expected results, on the single env
+        a = whole.random_legal_actions(9, t)
+        for g in range(2):
+            host_a[g][t].copy_(a[g * half:(g + 1) * half])
+        _, r, d = whole.step_autoreset(a, materialise=False)
+        want.append((r.cpu(), d.cpu()))
+    torch.cuda.synchronize()
+    for g in range(2):
+        with torch.cuda.stream(streams[g]):
+            groups[g].reset()
+    pending = [None, None]
+    for t in range(steps + 1):
+        for g in range(2):
+            if pending[g] is not None:            # results of this group's previous step
+                streams[g].synchronize()
+                tt, r, d = pending[g]
+                assert torch.equal(r, want[tt][0][g * half:(g + 1) * half]) and torch.equal(d, want[tt][1][g * half:(g + 1) * half])
+                pending[g] = None
+            if t < steps:
+                with torch.cuda.stream(streams[g]):
+                    _, r, d = groups[g].step_host(host_a[g][t], host_out[g][t % 2], autoreset=True, zero_copy=(g == 0),
+                                                  sync=False, out=(None, None))
+                pending[g] = (t, r, d)
+    torch.cuda.synchronize()
+    bits = whole._bits.view(2, -1, 2 * half)
+    for g in range(2):
+        assert torch.equal(groups[g]._bits.view(2, -1, half), bits[:, :, g * half:(g + 1) * half])
+
+
 def test_tournament_style_consumer_on_raw_env():
     """Second consumer of the env in the reference: MatchRunner._play_batch_games
     (src/model_comparison/match_runner.py:125-218) drives the RAW env -- reads env.current_player every
