@@ -16,6 +16,7 @@ env.reset()
 for t in range(20):
     env.step_autoreset(env.random_legal_actions(1, t), materialise=False)
 native._err = torch.zeros(1 + 8 * 16, dtype=torch.int32, device="cuda")
+native.use_rows_kernel = False          # this tool times the tap kernel (mnk_resnet.cu)
 for _ in range(3):
     native.features(env._st, ne, m * n, None)
 torch.cuda.synchronize()
