@@ -126,7 +126,19 @@ observe_kernel(G g, mnk_state_t st, float* __restrict__ obs, u8* __restrict__ ma
     const bool stream = tile_streams<G>(tile_envs, obs, mask);   // block-uniform
     u64 obsd[G::NWD];
     u64 legd[G::NWL];
-    if (threadIdx.x < 32) {
+    const int warp = threadIdx.x >> 5;
+    if (stream) {
+        // full tile on the stream path: warp 0 builds the observation bits, warp 1 the legal-cell bits, concurrently
+        // (the same split as step_dense_kernel's view warps); both read the state, nobody writes it
+        if ((warp == 0 && obs != nullptr) || (warp == 1 && mask != nullptr)) {
+            const long long e = e0 + lane;
+            EnvRegs<G> s;
+            env_load(st, e, s);
+            if (warp == 0) build_obs_view(g, s, swap != nullptr && swap[e] != 0, obsd);
+            else build_legal_view(g, s, fix_all_masked != 0, legd);
+        }
+        emit_block_stream_any(g, tile_smem, e0, obsd, legd, obs, mask, 0, 1);
+    } else if (warp == 0) {
         const long long e = e0 + lane;
         EnvRegs<G> s;
         env_zero(s);
@@ -136,9 +148,8 @@ observe_kernel(G g, mnk_state_t st, float* __restrict__ obs, u8* __restrict__ ma
             sw = swap != nullptr && swap[e] != 0;
         }
         build_views(g, s, sw, fix_all_masked != 0, obsd, legd);
-        if (!stream) emit_tile(g, e0, tile_envs, lane, obsd, legd, obs, mask);
+        emit_tile(g, e0, tile_envs, lane, obsd, legd, obs, mask);
     }
-    if (stream) emit_block_stream_any(g, tile_smem, e0, obsd, legd, obs, mask);
 }
 
 // ------------------------------------------------------------------------------------------------
