@@ -207,9 +207,11 @@ int mnk_rollout_gather(int32_t m, int32_t n, int32_t k, const uint64_t* packed, 
                        int64_t count, float* obs, uint8_t* mask, void* stream);
 
 /* RolloutBuffer.compute_advantages_and_returns (:60-80): GAE(lambda) over [steps][num_envs] arrays,
- * bit-identical in fp32 to the reference's tensor expressions. */
+ * bit-identical in fp32 to the reference's tensor expressions.  gamma / gae_lambda are the reference's Python
+ * floats (doubles): gamma enters the fp32 arithmetic as (float)gamma, their product as (float)(gamma * gae_lambda)
+ * -- multiplied in double first, as `gamma * gae_lambda * tensor` evaluates in Python (:76). */
 int mnk_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int64_t steps,
-            int64_t num_envs, float gamma, float gae_lambda, float* advantages, float* returns, void* stream);
+            int64_t num_envs, double gamma, double gae_lambda, float* advantages, float* returns, void* stream);
 
 /* PPOAgent.learn's episode accounting (ppo.py:110-120) without per-step host reads: ep_reward /
  * ep_len f32[num_envs] running sums, totals f64[6] += {episodes, sum reward, sum length, wins,

@@ -292,11 +292,13 @@ def gae(rewards, values, dones, last_values, gamma, lam):
     steps, n = rewards.shape
     adv = np.zeros((steps, n), dtype=f)
     last_gae = np.zeros(n, dtype=f)
-    gamma, lam = f(gamma), f(lam)
+    # gamma * gae_lambda is a product of two Python floats (double) before it meets an fp32 tensor (:76)
+    gl = f(float(gamma) * float(lam))
+    gamma = f(gamma)
     for t in reversed(range(steps)):
         next_values = last_values.astype(f) if t == steps - 1 else values[t + 1]
         nnt = f(1.0) - dones[t].astype(f)
         delta = rewards[t] + gamma * next_values * nnt - values[t]
-        last_gae = delta + gamma * lam * nnt * last_gae
+        last_gae = delta + gl * nnt * last_gae
         adv[t] = last_gae
     return adv, adv + values

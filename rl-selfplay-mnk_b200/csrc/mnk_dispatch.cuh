@@ -70,6 +70,22 @@ static inline int mnk_optin_smem(Kernel kernel, size_t bytes, std::atomic<size_t
     return MNK_OK;
 }
 
+// SM count of the current device (cached per device; 148 on B200) for persistent grids
+static inline int mnk_sm_count() {
+    static std::atomic<int> cached[kMaxDevices];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    const bool tracked = dev >= 0 && dev < kMaxDevices;
+    if (tracked) {
+        const int c = cached[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+    if (tracked) cached[dev].store(sms, std::memory_order_relaxed);
+    return sms;
+}
+
 // warp-tile kernels (pack): one warp per 32 consecutive envs, 4 warps per CTA
 constexpr int kTileEnvs = 32;
 constexpr int kTileWarps = 4;

@@ -216,7 +216,7 @@ import_meta_kernel(mnk_state_t st, const int64_t* __restrict__ player, const int
 // ------------------------------------------------------------------------------------------------
 template <class G>
 __global__ void __launch_bounds__(kFlatThreads)
-random_legal_kernel(G g, mnk_state_t st, u64 seed, u32 counter, long long env_offset, int deterministic,
+random_legal_kernel(G g, mnk_state_t st, u64 seed, u64 counter, long long env_offset, int deterministic,
                     int64_t* __restrict__ actions) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= st.num_envs) return;
@@ -395,7 +395,7 @@ int mnk_random_legal(const mnk_state_t* st, uint64_t seed, uint64_t counter, int
     if (st->num_envs == 0) return MNK_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return mnk_dispatch_geom(*st, [&](auto g) {
-        random_legal_kernel<<<mnk_flat_blocks(st->num_envs), kFlatThreads, 0, s>>>(g, *st, seed, (u32)counter, env_offset,
+        random_legal_kernel<<<mnk_flat_blocks(st->num_envs), kFlatThreads, 0, s>>>(g, *st, seed, counter, env_offset,
                                                                                  deterministic, actions);
         return mnk_launch_status();
     });

@@ -242,11 +242,11 @@ extern "C" int mnk_resnet_heads(const float* policy_feat, const float* value_fea
     const long long batches = (rows + hd::kSB - 1) / hd::kSB;
     auto launch = [&](auto kernel, std::atomic<size_t>* granted) {
         if (int rc = mnk_optin_smem(kernel, smem, granted)) return rc;
-        // persistent grid: exactly the CTAs that are resident at once on the 148 SMs (one wave, no tail)
+        // persistent grid: exactly the CTAs that are resident at once on the device's SMs (one wave, no tail)
         int per_sm = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, hd::kThreads, smem);
         if (e != cudaSuccess) return (int)e;
-        const long long resident = 148LL * (per_sm > 0 ? per_sm : 1);
+        const long long resident = (long long)mnk_sm_count() * (per_sm > 0 ? per_sm : 1);
         const unsigned grid = (unsigned)(batches < resident ? batches : resident);
         kernel<<<grid, hd::kThreads, smem, static_cast<cudaStream_t>(stream)>>>(policy_feat, value_feat, rows, cells, *w, logits,
                                                                                 values);

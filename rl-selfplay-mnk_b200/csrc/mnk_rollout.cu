@@ -64,13 +64,14 @@ rollout_gather_kernel(G g, const u64* __restrict__ packed, long long num_envs, c
 // tensor expressions (no fused multiply-add) so results are bit-identical to it in fp32.
 __global__ void __launch_bounds__(kFlatThreads)
 gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const u8* __restrict__ dones,
-           const float* __restrict__ last_values, long long steps, long long num_envs, float gamma, float lambda,
+           const float* __restrict__ last_values, long long steps, long long num_envs, float gamma, float gl,
            float* __restrict__ advantages, float* __restrict__ returns) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= num_envs) return;
     float last_gae = 0.0f;
     float next_value = last_values[e];
-    const float gl = __fmul_rn(gamma, lambda);
+    // gl = (float)(gamma * lambda) with the product taken in DOUBLE on the host: the reference multiplies the two
+    // Python floats first and only then meets an fp32 tensor (rollout_buffer.py:76)
     for (long long t = steps - 1; t >= 0; --t) {
         const size_t i = (size_t)t * num_envs + e;
         const float nnt = 1.0f - (dones[i] ? 1.0f : 0.0f);
@@ -142,12 +143,12 @@ int mnk_rollout_gather(int32_t m, int32_t n, int32_t k, const uint64_t* packed, 
 }
 
 int mnk_gae(const float* rewards, const float* values, const uint8_t* dones, const float* last_values, int64_t steps,
-            int64_t num_envs, float gamma, float gae_lambda, float* advantages, float* returns, void* stream) {
+            int64_t num_envs, double gamma, double gae_lambda, float* advantages, float* returns, void* stream) {
     if (!rewards || !values || !dones || !last_values || !advantages || !returns) return MNK_ERR_NULL;
     if (steps < 0 || num_envs < 0) return MNK_ERR_ARG;
     if (steps == 0 || num_envs == 0) return MNK_OK;
     gae_kernel<<<mnk_flat_blocks(num_envs), kFlatThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        rewards, values, dones, last_values, steps, num_envs, gamma, gae_lambda, advantages, returns);
+        rewards, values, dones, last_values, steps, num_envs, (float)gamma, (float)(gamma * gae_lambda), advantages, returns);
     return mnk_launch_status();
 }
 

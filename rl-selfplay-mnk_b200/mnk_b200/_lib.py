@@ -111,7 +111,7 @@ SIGNATURES = {
     "mnk_selfplay_step_random": (_I32, [_ST, _SP, _VP, _VP, _U64, _VP, _VP, _VP, _VP, _U32, _VP]),
     "mnk_rollout_store_obs": (_I32, [_ST, _VP, _VP, _VP]),
     "mnk_rollout_gather": (_I32, [_I32, _I32, _I32, _VP, _I64, _VP, _I64, _VP, _VP, _VP]),
-    "mnk_gae": (_I32, [_VP, _VP, _VP, _VP, _I64, _I64, ctypes.c_float, ctypes.c_float, _VP, _VP, _VP]),
+    "mnk_gae": (_I32, [_VP, _VP, _VP, _VP, _I64, _I64, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP]),
     "mnk_episode_stats": (_I32, [_VP, _VP, _I64, _VP, _VP, _VP, _VP]),
     "mnk_resnet_tower": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "mnk_resnet_tower_rows": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),

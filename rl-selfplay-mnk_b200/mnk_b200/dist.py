@@ -75,3 +75,29 @@ def global_mean_std(values: torch.Tensor, group=None):
     mean = moments[0] / moments[2]
     var = (moments[1] - moments[2] * mean * mean) / (moments[2] - 1).clamp(min=1)
     return mean.float(), var.clamp(min=0).sqrt().float()
+
+
+def common_minibatches(local_batches: int, world_size: int, group=None, device=None) -> int:
+    """The number of optimiser steps per epoch every rank can join: min over ranks of the local minibatch count
+    (ranks with uneven shards would otherwise issue different numbers of gradient all-reduces and hang)."""
+    if world_size <= 1:
+        return int(local_batches)
+    t = torch.tensor([int(local_batches)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return int(t.item())
+
+
+def broadcast_module(module: torch.nn.Module, optimizer=None, src: int = 0, group=None) -> None:
+    """Data-parallel start-up: every replica takes rank `src`'s parameters and buffers (BatchNorm statistics
+    included) and, if given, its optimiser's tensor state -- the ranks then stay in lock-step through
+    average_gradients without relying on identical seeding."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+        if optimizer is not None:
+            for state in optimizer.state.values():
+                for v in state.values():
+                    if torch.is_tensor(v):
+                        dist.broadcast(v, src=src, group=group)

@@ -17,6 +17,7 @@ training hot path never touches them and pays nothing.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -30,7 +31,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class TorchVectorMnkEnv:
-    def __init__(self, m: int, n: int, k: int, num_envs: int, device: str = "cuda", strict: bool = False,
+    def __init__(self, m: int, n: int, k: int, num_envs: int, device: str = "cuda", strict: Optional[bool] = None,
                  env_offset: int = 0):
         assert m >= k and n >= k, f"Board ({m}x{n}) is too small for k={k}"   # reference :9
         self.m, self.n, self.k = int(m), int(n), int(k)
@@ -45,7 +46,10 @@ class TorchVectorMnkEnv:
         self._L = _lib.lib()
         words = self._L.mnk_state_words(self.m, self.n)
         check(words if words < 0 else 0, "TorchVectorMnkEnv")
-        self.strict = bool(strict)
+        # strict: raise the reference's (dead-code) ValueErrors on illegal / out-of-range moves, :86-104.  Default off --
+        # the reference applies such moves silently -- or MNK_B200_STRICT=1 in the environment.
+        self.strict = bool(int(os.environ.get("MNK_B200_STRICT", "0"))) if strict is None else bool(strict)
+        self._illegal: Optional[torch.Tensor] = None     # i32[2] strict-mode counters written by the step kernels
         self.env_offset = int(env_offset)     # global id of local env 0 (sharded runs)
         self.max_moves = self.m * self.n
         self.env_indices = torch.arange(self.num_envs, device=self._dev)
@@ -187,8 +191,12 @@ class TorchVectorMnkEnv:
                 raise ValueError(f"step_subset: {a.numel()} actions for {idx.numel()} indices")
         elif a.numel() != self.num_envs:
             raise ValueError(f"step: expected {self.num_envs} actions, got {a.numel()}")
+        illegal = None
         if self.strict:
-            self._validate(a, idx)
+            if self._illegal is None:
+                self._illegal = torch.zeros(2, dtype=torch.int32, device=self._dev)
+            illegal = self._illegal
+            illegal.zero_()
         if autoreset:
             flags |= _lib.STEP_AUTORESET
         rewards = torch.empty(self.num_envs, dtype=torch.float32, device=self._dev)
@@ -205,23 +213,27 @@ class TorchVectorMnkEnv:
                 self._call(self._L.mnk_observe, _ptr(obs), _ptr(mask), None, 0)
             return {"observation": obs, "action_mask": mask}, rewards, dones
         self._call(self._L.mnk_step, _ptr(a), _ptr(idx), a.numel(), _ptr(rewards), _ptr(dones), _ptr(obs), _ptr(mask),
-                   None, flags)
+                   _ptr(illegal), flags)
         self._refresh_mirrors()
+        if illegal is not None:
+            self._raise_if_illegal(a, idx)
         return {"observation": obs, "action_mask": mask}, rewards, dones
 
-    def _validate(self, a: torch.Tensor, idx: Optional[torch.Tensor]):
-        """Opt-in legality check with the reference's (dead-code) messages, :86-104."""
+    def _raise_if_illegal(self, a: torch.Tensor, idx: Optional[torch.Tensor]):
+        """Opt-in legality check with the reference's (dead-code) messages, :86-104.  The step kernel counts
+        moves onto occupied / out-of-range cells into a device flag (include/mnk_b200.h, `illegal`); strict mode
+        costs ONE device->host read of that flag per step.  The offending moves have been applied exactly as in
+        the default mode (occupied cell: stone written over; out of range: no stone) when the error is raised."""
+        count, key = self._illegal.tolist()
+        if count == 0:
+            return
+        env_id = 0x7FFFFFFF - key                           # smallest offending env index
+        pos = env_id if idx is None else int(torch.nonzero(idx == env_id)[0])
+        val = int(a[pos])
         cells = self.m * self.n
-        bad = (a < 0) | (a >= cells)
-        if bad.any():
-            val = a[torch.nonzero(bad)[0]].item()
+        if val < 0 or val >= cells:
             raise ValueError(f"Action out of bounds! Env received {val}, expected [0, {cells - 1}]")
-        mask = self._observe_packed()["action_mask"]
-        rows = self.env_indices if idx is None else idx
-        occupied = ~mask[rows, a.long()]
-        if occupied.any():
-            env_id = rows[torch.nonzero(occupied)[0]].item()
-            raise ValueError(f"Illegal Move: Env {env_id} tried to play in occupied cell.")
+        raise ValueError(f"Illegal Move: Env {env_id} tried to play in occupied cell.")
 
     # ------------------------------------------------------------------ extensions (not in the reference)
     def step_autoreset(self, actions: torch.Tensor, materialise: bool = True, out=None):

@@ -11,12 +11,12 @@ from __future__ import annotations
 
 import itertools
 from abc import ABC, abstractmethod
-from typing import Dict
+from typing import Dict, Optional
 
 import torch
 import torch.nn as nn
 
-from .sampling import MaskedCategorical, masked_sample
+from .sampling import MaskedCategorical, fresh_seed, masked_sample
 
 
 class Policy(ABC):
@@ -29,9 +29,9 @@ class RandomPolicy(Policy):
     """Uniform over legal cells; rows with no legal cell draw uniformly from all cells (the reference adds
     1e-8 to every entry of such rows, policy.py:21-24); deterministic => first legal cell (:26-27)."""
 
-    def __init__(self, action_dim: int, seed: int = 0):
+    def __init__(self, action_dim: int, seed: Optional[int] = None):
         self.action_dim = action_dim
-        self.seed = seed
+        self.seed = fresh_seed() if seed is None else seed
         self._calls = itertools.count(1)
 
     def act(self, obs: Dict[str, torch.Tensor], deterministic: bool = False) -> torch.Tensor:
@@ -44,10 +44,10 @@ class RandomPolicy(Policy):
 
 
 class NNPolicy(Policy):
-    def __init__(self, model: nn.Module, seed: int = 0):
+    def __init__(self, model: nn.Module, seed: Optional[int] = None):
         self.model = model
         self.model.eval()                       # policy.py:33-35
-        self.seed = seed
+        self.seed = fresh_seed() if seed is None else seed
         self._calls = itertools.count(1)
 
     def act(self, obs: Dict[str, torch.Tensor], deterministic: bool = False) -> torch.Tensor:

@@ -20,7 +20,7 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
-from .dist import average_gradients, global_mean_std
+from .dist import average_gradients, broadcast_module, common_minibatches, global_mean_std
 from .rollout import RolloutBuffer, RolloutCollector
 
 
@@ -60,6 +60,8 @@ class PPOAgent:
         self.buffer = RolloutBuffer(n_steps, num_envs, obs_shape, action_dim, device=device, k=k)
         self.collector = RolloutCollector(num_envs, device=device, seed=seed, row_offset=env_offset,
                                           process_group=process_group, world_size=world_size)
+        if world_size > 1:          # replicas start from rank 0's parameters / buffers / optimiser state
+            broadcast_module(self.network, self.optimizer, group=process_group)
 
     # ------------------------------------------------------------------ reference :78-166
     def learn(self, vec_env) -> TrainingMetrics:
@@ -88,9 +90,14 @@ class PPOAgent:
         buf = self.buffer
         # global advantage statistics (== the single-process normalisation of rollout_buffer.py:96-99)
         adv_mean, adv_std = global_mean_std(buf.advantages[:buf.ptr], group=self.group)
+        # every rank must join the same number of gradient all-reduces: with uneven shards the ranks agree on the
+        # smallest minibatch count (all-reduce MIN) and the longer loaders drop their last batches
+        n_batches = common_minibatches(-(-buf.ptr * buf.num_envs // self.batch_size), self.world_size, self.group, dev)
         for _ in range(self.ppo_epochs):
-            for obs, actions, old_log_probs, returns, advantages, masks, _old_values in buf.get_data_loader(
-                    self.batch_size, normalize_advantages=False):
+            for b, (obs, actions, old_log_probs, returns, advantages, masks, _old_values) in enumerate(buf.get_data_loader(
+                    self.batch_size, normalize_advantages=False)):
+                if b >= n_batches:
+                    break
                 advantages = (advantages - adv_mean) / (adv_std + 1e-8)
                 self.optimizer.zero_grad(set_to_none=True)
                 with torch.autocast("cuda", dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):

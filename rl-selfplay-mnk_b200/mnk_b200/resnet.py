@@ -20,7 +20,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import MnkHeadsWeights, MnkState, check
 from .policy import Policy
-from .sampling import MaskedCategorical, masked_sample
+from .sampling import MaskedCategorical, fresh_seed, masked_sample
 
 
 def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -165,10 +165,10 @@ class NativeResNet:
 class NativeNNPolicy(Policy):
     """NNPolicy (src/selfplay/policy.py:32-54) on the tcgen05 forward."""
 
-    def __init__(self, model: nn.Module, device="cuda", seed: int = 0):
+    def __init__(self, model: nn.Module, device="cuda", seed: Optional[int] = None):
         model.eval()
         self.net = NativeResNet(model, device=device)
-        self.seed = seed
+        self.seed = fresh_seed() if seed is None else seed
         self._calls = 0
         self.counter_base: Optional[torch.Tensor] = None     # see TorchSelfPlayWrapper.counter_base
 

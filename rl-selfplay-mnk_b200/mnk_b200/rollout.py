@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 from ._lib import MnkState, check
-from .sampling import MaskedCategorical, masked_sample
+from .sampling import MaskedCategorical, fresh_seed, masked_sample
 
 _STATIC_K = {(3, 3): 3, (9, 9): 5, (13, 13): 5, (15, 15): 5, (19, 19): 5}
 
@@ -181,11 +181,11 @@ class RolloutStats:
 class RolloutCollector:
     """The rollout half of PPOAgent.learn (src/alg/ppo.py:78-133)."""
 
-    def __init__(self, num_envs: int, device="cuda", seed: int = 0, row_offset: int = 0, process_group=None,
+    def __init__(self, num_envs: int, device="cuda", seed: Optional[int] = None, row_offset: int = 0, process_group=None,
                  world_size: int = 1):
         self.num_envs = num_envs
         self._dev = torch.device(device)
-        self.seed, self.row_offset = seed, row_offset
+        self.seed, self.row_offset = (fresh_seed() if seed is None else seed), row_offset
         self.group, self.world_size = process_group, world_size
         self._L = _lib.lib()
         self._last_obs = None
@@ -219,8 +219,16 @@ class RolloutCollector:
         the Philox counters baked into the captured launches are offset by a device-resident base that is
         bumped before each replay, so every replay draws fresh numbers.  Removes the per-launch host overhead
         (decisive at small batch: the reference's default is 384 envs)."""
-        key = (id(network), id(vec_env), id(buffer), steps, id(vec_env.opponent_policy))
-        if getattr(self, "_graph_key", None) != key:
+        # The graph bakes raw device pointers (weights, state, buffer slots).  The key holds STRONG references to the
+        # captured objects (an id() can be recycled once its object dies) plus their pointer signatures: NativeResNet
+        # keeps its weight tensors at stable addresses across refresh() and reports any re-allocation through
+        # `pointer_signature()`, so a replay can never read freed or stale weight storage.
+        opp = vec_env.opponent_policy
+        sig = tuple(o.pointer_signature() if hasattr(o, "pointer_signature") else None
+                    for o in (network, getattr(opp, "net", None)))
+        key = (network, vec_env, buffer, steps, opp, sig, buffer.packed_obs.data_ptr(), vec_env.env._bits.data_ptr())
+        old = getattr(self, "_graph_key", None)
+        if old is None or len(old) != len(key) or any(a is not b and a != b for a, b in zip(old, key)):
             with torch.no_grad():                          # one-time work that must not happen under capture
                 network.forward_env(vec_env.env, swap=vec_env._side)
                 opp = vec_env.opponent_policy
@@ -291,7 +299,13 @@ class RolloutCollector:
             import torch.distributed as dist_mod
             totals = totals.clone()                        # (the graph's accumulator stays rank-local)
             dist_mod.all_reduce(totals, op=dist_mod.ReduceOp.SUM, group=self.group)
-        tot = totals.tolist()                              # one device->host read per rollout
+        # one device->host read per rollout; it also carries the tcgen05 kernels' "internal barrier wait timed out"
+        # flags, so a poisoned forward cannot silently fill the buffer with garbage features
+        flags = [o._err for o in (network, getattr(vec_env.opponent_policy, "net", None)) if hasattr(o, "_err")]
+        tot = torch.cat([totals] + [f.double() for f in flags]).tolist()
+        if any(v != 0.0 for v in tot[6:]):
+            raise RuntimeError("mnk_b200: a tcgen05 tower launch of this rollout hit an internal barrier timeout; "
+                               "its features (and everything sampled from them) are invalid")
         elapsed = time.time() - start
         agent_steps = steps * self.num_envs * self.world_size
         episodes = tot[0]

@@ -16,6 +16,20 @@ import torch
 from . import _lib
 
 _auto_counter = itertools.count(1)
+_seed_counter = itertools.count(1)
+
+
+def fresh_seed() -> int:
+    """A distinct 64-bit Philox key per call (splitmix64 of a process-wide counter): the default seed of every
+    sampler-owning object (RandomPolicy, NNPolicy, NativeNNPolicy, RolloutCollector, MaskedCategorical).  The draws
+    are keyed by (seed, global row, counter), and the counters are small per-object call counts -- two objects
+    sharing one default seed would hand consecutive plies of a game (agent's draw at step t, opponent's at t) the
+    same noise.  Pass an explicit seed for reproducible streams; ranks of a sharded run get the same sequence of
+    default seeds and differ by their global row offsets."""
+    z = (next(_seed_counter) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
 
 
 def masked_sample(logits: torch.Tensor, mask: Optional[torch.Tensor], seed: int = 0, counter: Optional[int] = None,
@@ -59,10 +73,10 @@ def masked_sample(logits: torch.Tensor, mask: Optional[torch.Tensor], seed: int 
 class MaskedCategorical:
     """Categorical(logits=where(mask, logits, -inf)) with all-masked rows made uniform."""
 
-    def __init__(self, logits: torch.Tensor, action_mask: Optional[torch.Tensor] = None, seed: int = 0):
+    def __init__(self, logits: torch.Tensor, action_mask: Optional[torch.Tensor] = None, seed: Optional[int] = None):
         self._raw = logits
         self._mask = action_mask
-        self._seed = seed
+        self._seed = fresh_seed() if seed is None else seed
         self._normalised: Optional[torch.Tensor] = None
 
     def sample(self) -> torch.Tensor:

@@ -27,10 +27,11 @@ from . import _lib
 from ._lib import MnkSelfplay, check
 from .env import TorchVectorMnkEnv, _ptr
 from .policy import RandomPolicy
+from .sampling import fresh_seed
 
 
 class TorchSelfPlayWrapper:
-    def __init__(self, env: TorchVectorMnkEnv, seed: int = 0):
+    def __init__(self, env: TorchVectorMnkEnv, seed: Optional[int] = None):
         self.env = env
         self.device = env.device
         self.num_envs = env.num_envs
@@ -38,7 +39,7 @@ class TorchSelfPlayWrapper:
         dev = env._dev
         self._dev = dev
         self._L = _lib.lib()
-        self.seed = int(seed)
+        self.seed = fresh_seed() if seed is None else int(seed)   # keys the side draws and the fused random opponent
         self._side = torch.zeros(self.num_envs, dtype=torch.uint8, device=dev)
         self.pending_resets = torch.zeros(self.num_envs, dtype=torch.bool, device=dev)    # reference :14
         self._episodes = torch.zeros(self.num_envs, dtype=torch.int32, device=dev)
@@ -49,16 +50,31 @@ class TorchSelfPlayWrapper:
         self._opp_active = torch.zeros(self.num_envs, dtype=torch.uint8, device=dev)
         self._steps = 0
         self.next_sides: Optional[torch.Tensor] = None   # i64[N]: sides for envs reset by the NEXT step (else Philox)
+        self._side_mirror: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ reference attributes
     @property
     def agent_side(self) -> torch.Tensor:
-        """i64[N], 0 = black, 1 = white (reference :13).  A copy; assign to set."""
-        return self._side.long()
+        """i64[N], 0 = black, 1 = white (reference :13).  A live, writable mirror of the u8 sides the kernels
+        use (like env.boards): created on first access, folded back before every wrapper operation (so in-place
+        writes such as ``wrapper.agent_side[:] = 1`` take effect) and refreshed afterwards."""
+        if self._side_mirror is None:
+            self._side_mirror = self._side.long()
+        return self._side_mirror
 
     @agent_side.setter
     def agent_side(self, value):
         self._side.copy_(torch.as_tensor(value, device=self._dev).to(torch.uint8).expand(self.num_envs))
+        if self._side_mirror is not None:
+            self._side_mirror.copy_(self._side)
+
+    def _fold_side(self):
+        if self._side_mirror is not None:
+            self._side.copy_(self._side_mirror)
+
+    def _refresh_side(self):
+        if self._side_mirror is not None:
+            self._side_mirror.copy_(self._side)
 
     def set_opponent(self, policy):
         self.opponent_policy = policy
@@ -91,6 +107,7 @@ class TorchSelfPlayWrapper:
              materialise: bool = True):
         env = self.env
         env._fold_mirrors()
+        self._fold_side()
         flags = _lib.SP_RESET_ALL if reset_all else 0
         a = None
         if actions is not None:
@@ -139,6 +156,7 @@ class TorchSelfPlayWrapper:
                                                      _ptr(terminated), _ptr(obs), _ptr(mask), oflags, self._stream()),
                       "mnk_selfplay_opponent")
         env._refresh_mirrors()
+        self._refresh_side()
         return {"observation": obs, "action_mask": mask}, rewards, terminated
 
     # ------------------------------------------------------------------ reference methods
@@ -162,6 +180,7 @@ class TorchSelfPlayWrapper:
     def get_agent_obs(self) -> Dict[str, torch.Tensor]:
         """reference :99-115"""
         self.env._fold_mirrors()
+        self._fold_side()
         return self.env._observe_packed(swap=self._side, fix_all_masked=True)
 
     _get_canonical_obs = get_agent_obs

@@ -15,9 +15,39 @@ from mnk_b200 import dist as mdist
 
 def test_oracle_gae_matches_reference_buffer():
     g = gio.load(gio.files("rollout_buffer_gae")[0])
-    adv, ret = orc.gae(g["rewards"], g["values"], g["dones"], g["last_values"], float(g["gamma"]), float(g["lam"]))
+    adv, ret = orc.gae(g["rewards"], g["values"], g["dones"], g["last_values"], round(float(g["gamma"]), 6), round(float(g["lam"]), 6))
     assert np.array_equal(adv, g["advantages"]) and np.array_equal(ret, g["returns"])
     assert np.array_equal(g["stored_obs"], g["obs"]) and np.array_equal(g["stored_masks"], g["masks"])
+
+
+GAE_PAIRS = [(0.99, 0.95), (0.997, 0.9), (0.9, 0.97), (0.993, 0.913), (1.0, 1.0), (0.95, 0.0)]
+
+
+def test_gae_pairs_include_one_where_float_product_differs():
+    """gamma * gae_lambda is multiplied in double and THEN rounded to fp32 by the reference (rollout_buffer.py:76);
+    multiplying the fp32 roundings instead is off by one ulp for some pairs -- make sure the list has such a pair."""
+    f = np.float32
+    assert any(f(f(g) * f(l)) != f(g * l) for g, l in GAE_PAIRS)
+
+
+@pytest.mark.parametrize("gamma,lam", GAE_PAIRS)
+def test_oracle_gae_matches_live_reference_buffer(gamma, lam):
+    from oracle import ref_tree
+    if not ref_tree.available():
+        pytest.skip("reference tree neither mounted nor staged (oracle/_ref)")
+    rb = ref_tree.load("alg.rollout_buffer")
+    rng = np.random.default_rng(11)
+    steps, ne = 23, 257
+    buf = rb.RolloutBuffer(steps, ne, (2, 3, 3), 9, device="cpu")
+    rewards = rng.choice([-1.0, 0.0, 1.0], size=(steps, ne)).astype(np.float32)
+    values = rng.normal(size=(steps, ne)).astype(np.float32)
+    dones = rng.random((steps, ne)) < 0.1
+    last = rng.normal(size=ne).astype(np.float32)
+    buf.rewards.copy_(torch.from_numpy(rewards)), buf.values.copy_(torch.from_numpy(values)), buf.dones.copy_(torch.from_numpy(dones))
+    buf.ptr = steps
+    buf.compute_advantages_and_returns(torch.from_numpy(last), gamma, lam)
+    adv, ret = orc.gae(rewards, values, dones, last, gamma, lam)
+    assert np.array_equal(adv, buf.advantages.numpy()) and np.array_equal(ret, buf.returns.numpy())
 
 
 def test_shard_partition():

@@ -28,7 +28,7 @@ def test_buffer_add_gae_and_gather_match_reference_buffer():
                 t(g["dones"][s]), t(masks[s]))
     with pytest.raises(IndexError):
         buf.add(t(obs[0]), t(g["actions"][0]), t(g["rewards"][0]), t(g["values"][0]), t(g["log_probs"][0]), t(g["dones"][0]))
-    buf.compute_advantages_and_returns(t(g["last_values"]), float(g["gamma"]), float(g["lam"]))
+    buf.compute_advantages_and_returns(t(g["last_values"]), round(float(g["gamma"]), 6), round(float(g["lam"]), 6))
     assert np.array_equal(buf.advantages.cpu().numpy(), g["advantages"])
     assert np.array_equal(buf.returns.cpu().numpy(), g["returns"])
     assert np.array_equal(buf.observations.cpu().numpy(), obs)
@@ -51,7 +51,10 @@ def test_buffer_add_gae_and_gather_match_reference_buffer():
     assert buf.ptr == 0 and buf.rewards.abs().sum().item() == 0
 
 
-def test_gae_kernel_large_random_vs_oracle():
+@pytest.mark.parametrize("gamma,lam", [(0.99, 0.95), (0.997, 0.9), (0.9, 0.97), (0.993, 0.913), (1.0, 1.0), (0.95, 0.0)])
+def test_gae_kernel_large_random_vs_oracle(gamma, lam):
+    """The oracle's GAE is pinned to the live reference buffer for the same (gamma, lambda) pairs in
+    tests/test_rollout_cpu.py, including pairs where (float)gamma * (float)lambda != (float)(gamma * lambda)."""
     from mnk_b200 import RolloutBuffer
     rng = np.random.default_rng(4)
     steps, ne = 128, 4099
@@ -62,8 +65,8 @@ def test_gae_kernel_large_random_vs_oracle():
     last = rng.normal(size=ne).astype(np.float32)
     buf.rewards.copy_(t(rewards)), buf.values.copy_(t(values)), buf.dones.copy_(t(dones))
     buf.ptr = steps
-    buf.compute_advantages_and_returns(t(last), 0.99, 0.95)
-    adv, ret = orc.gae(rewards, values, dones, last, 0.99, 0.95)
+    buf.compute_advantages_and_returns(t(last), gamma, lam)
+    adv, ret = orc.gae(rewards, values, dones, last, gamma, lam)
     assert np.array_equal(buf.advantages.cpu().numpy(), adv) and np.array_equal(buf.returns.cpu().numpy(), ret)
 
 
