@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MNK_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+#define MNK_B200_VERSION 200 /* major*10000 + minor*100 + patch */
 
 #define MNK_OK 0
 #define MNK_ERR_NULL (-1)     /* a required pointer is NULL */
@@ -114,6 +114,30 @@ int mnk_step(const mnk_state_t* st, const void* actions, const int64_t* idx, int
  * synchronise to the caller. */
 int mnk_step_host(const mnk_state_t* st, const void* host_actions, void* dev_actions, void* dev_rd,
                   void* host_rd, float* obs, uint8_t* mask, uint32_t flags, void* stream);
+
+/* K dense steps per call for callers whose actions are already in pinned host memory (a recorded trace, an
+ * evaluation script, a host policy working one slab ahead): TorchVectorMnkEnv.step (:55-84) applied `steps` times,
+ * pipelined over slabs of `slab_steps` steps -- H2D of slab i+1 | kernels of slab i | D2H of slab i-1 on three
+ * streams, ONE cudaMemcpyAsync per slab and direction and ONE host wait per slab (csrc/mnk_hostloop.cu).
+ * Synchronous: returns when host_rd (and host_obs / host_mask) hold all `steps` results. */
+typedef struct mnk_host_loop {
+    const void* host_actions;   /* pinned  i64|i32 [steps][num_envs]                                              */
+    void* host_rd;              /* pinned  [steps][5*num_envs] bytes: per step f32 rewards[num_envs], u8 dones[num_envs] */
+    float* host_obs;            /* NULL, or pinned f32 [steps][num_envs][2][m][n]: also bring every observation home */
+    uint8_t* host_mask;         /* NULL, or pinned u8  [steps][num_envs][m*n]                                     */
+    void* dev_actions;          /* device scratch [2][slab_steps][num_envs] actions                               */
+    void* dev_rd;               /* device scratch [2][slab_steps][5*num_envs] bytes                               */
+    float* const* obs_ring;     /* host array of `ring` device pointers f32[num_envs][2][m][n]: step t materialises */
+    uint8_t* const* mask_ring;  /*   its observation / mask into slot t % ring (ring == 0: packed mode, no views) */
+    int32_t ring;               /* >= 2 * slab_steps when host_obs / host_mask are set                            */
+    int64_t steps, slab_steps;
+} mnk_host_loop_t;
+
+/* Streams + events of the pipeline, owned by the caller (create once, reuse across calls on the same device). */
+int mnk_host_pipe_create(void** pipe);
+int mnk_host_pipe_destroy(void* pipe);
+/* flags: MNK_STEP_ACTIONS_I32, MNK_STEP_AUTORESET.  `pipe` may be NULL (a temporary one is made for the call). */
+int mnk_step_host_loop(const mnk_state_t* st, const mnk_host_loop_t* job, void* pipe, uint32_t flags, void* stream);
 
 /* `env.boards` (torch_vector_mnk_env.py:17) as a writable f32[num_envs][2][m][n] mirror:
  * unpack = bitboards -> f32 planes, pack = f32 planes (non-zero = stone) -> bitboards. */

@@ -38,6 +38,14 @@ class MnkSelfplay(ctypes.Structure):
                 ("seed", ctypes.c_uint64), ("env_offset", ctypes.c_int64), ("counter_base", ctypes.c_void_p)]
 
 
+class MnkHostLoop(ctypes.Structure):
+    """struct mnk_host_loop of include/mnk_b200.h."""
+    _fields_ = [("host_actions", ctypes.c_void_p), ("host_rd", ctypes.c_void_p), ("host_obs", ctypes.c_void_p),
+                ("host_mask", ctypes.c_void_p), ("dev_actions", ctypes.c_void_p), ("dev_rd", ctypes.c_void_p),
+                ("obs_ring", ctypes.POINTER(ctypes.c_void_p)), ("mask_ring", ctypes.POINTER(ctypes.c_void_p)),
+                ("ring", ctypes.c_int32), ("steps", ctypes.c_int64), ("slab_steps", ctypes.c_int64)]
+
+
 class MnkHeadsWeights(ctypes.Structure):
     """struct mnk_heads_weights of include/mnk_b200.h (16 device pointers)."""
     NAMES = ("p_ln1_w", "p_ln1_b", "p_w1t", "p_b1", "p_ln2_w", "p_ln2_b", "p_w2t", "p_b2",
@@ -100,6 +108,9 @@ SIGNATURES = {
     "mnk_observe": (_I32, [_ST, _VP, _VP, _VP, _I32, _VP]),
     "mnk_step": (_I32, [_ST, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
     "mnk_step_host": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
+    "mnk_host_pipe_create": (_I32, [ctypes.POINTER(ctypes.c_void_p)]),
+    "mnk_host_pipe_destroy": (_I32, [_VP]),
+    "mnk_step_host_loop": (_I32, [_ST, ctypes.POINTER(MnkHostLoop), _VP, _U32, _VP]),
     "mnk_unpack_boards": (_I32, [_ST, _VP, _VP]),
     "mnk_pack_boards": (_I32, [_ST, _VP, _VP]),
     "mnk_export_meta": (_I32, [_ST, _VP, _VP, _VP]),

@@ -287,6 +287,71 @@ class TorchVectorMnkEnv:
             self._host_views = {host_out.data_ptr(): views}
         return {"observation": obs, "action_mask": mask}, views[0], views[1]
 
+    def step_host_loop(self, host_actions: torch.Tensor, host_out: torch.Tensor, slab_steps: int = 4, autoreset: bool = False,
+                       ring: Optional[Tuple[list, list]] = None, host_obs: Optional[torch.Tensor] = None,
+                       host_mask: Optional[torch.Tensor] = None):
+        """K dense steps in ONE call of the C ABI (mnk_step_host_loop): `host_actions` pinned int64|int32 [K, N],
+        `host_out` pinned uint8 [K, 5*N] (per step f32 rewards then bool dones).  The library pipelines slabs of
+        `slab_steps` steps -- H2D of the next slab | the step kernels | D2H of the previous slab -- with one copy per
+        slab and direction and one host wait per slab.  `ring` = (obs_list, mask_list) of device tensors the steps
+        materialise their observation / mask into (step t -> slot t % len); None = packed mode.  `host_obs` /
+        `host_mask` (pinned f32 [K, N, 2, m, n] / bool [K, N, m*n]) additionally bring every step's views to the
+        host.  Returns (rewards f32 [K, N], dones bool [K, N]) as views of `host_out`."""
+        self._fold_mirrors()
+        n = self.num_envs
+        if host_actions.dim() != 2 or host_actions.shape[1] != n or not host_actions.is_contiguous():
+            raise ValueError(f"step_host_loop: host_actions must be a contiguous [K, {n}] tensor")
+        steps = host_actions.shape[0]
+        if host_out.dtype != torch.uint8 or host_out.numel() < steps * 5 * n or not host_out.is_contiguous():
+            raise ValueError("step_host_loop: host_out must be a contiguous uint8 tensor of at least K * 5 * N bytes")
+        if not (host_actions.is_pinned() and host_out.is_pinned()):
+            raise ValueError("step_host_loop needs pinned host tensors")
+        flags = _lib.STEP_AUTORESET if autoreset else 0
+        if host_actions.dtype == torch.int32:
+            flags |= _lib.STEP_ACTIONS_I32
+        elif host_actions.dtype != torch.long:
+            raise ValueError("step_host_loop: actions must be int64 or int32")
+        slab_steps = max(1, min(int(slab_steps), steps)) if steps else 1
+        key = (slab_steps, host_actions.dtype)
+        if getattr(self, "_loop_key", None) != key:      # device slabs (double-buffered) and the stream / event pipe
+            self._loop_dev_actions = torch.empty((2, slab_steps, n), dtype=host_actions.dtype, device=self._dev)
+            self._loop_dev_rd = torch.empty((2, slab_steps, 5 * n), dtype=torch.uint8, device=self._dev)
+            self._loop_key = key
+        if getattr(self, "_loop_pipe", None) is None:
+            pipe = ctypes.c_void_p()
+            with torch.cuda.device(self._dev):
+                check(self._L.mnk_host_pipe_create(ctypes.byref(pipe)), "mnk_host_pipe_create")
+            self._loop_pipe = pipe
+        job = _lib.MnkHostLoop()
+        job.host_actions, job.host_rd = host_actions.data_ptr(), host_out.data_ptr()
+        job.host_obs = None if host_obs is None else host_obs.data_ptr()
+        job.host_mask = None if host_mask is None else host_mask.data_ptr()
+        for t_ in (host_obs, host_mask):
+            if t_ is not None and not (t_.is_pinned() and t_.is_contiguous()):
+                raise ValueError("step_host_loop: host_obs / host_mask must be pinned and contiguous")
+        job.dev_actions, job.dev_rd = self._loop_dev_actions.data_ptr(), self._loop_dev_rd.data_ptr()
+        if ring is not None:
+            obs_list, mask_list = ring
+            cnt = len(obs_list)
+            arr_o = (ctypes.c_void_p * cnt)(*[o.data_ptr() for o in obs_list])
+            arr_m = (ctypes.c_void_p * cnt)(*[m_.data_ptr() for m_ in mask_list])
+            job.obs_ring, job.mask_ring, job.ring = arr_o, arr_m, cnt
+        else:
+            job.ring = 0
+        job.steps, job.slab_steps = steps, slab_steps
+        self._call(self._L.mnk_step_host_loop, ctypes.byref(job), self._loop_pipe, flags)
+        self._refresh_mirrors()
+        out = host_out.reshape(-1)[: steps * 5 * n].view(steps, 5 * n)
+        return out[:, : 4 * n].view(torch.float32), out[:, 4 * n:].view(torch.bool)
+
+    def __del__(self):
+        pipe = getattr(self, "_loop_pipe", None)
+        if pipe is not None:
+            try:
+                self._L.mnk_host_pipe_destroy(pipe)
+            except Exception:
+                pass
+
     def state_checksum(self) -> int:
         """Order-sensitive 64-bit digest of the packed state (used by bench.py / tests)."""
         self._fold_mirrors()

@@ -25,7 +25,7 @@ def test_header_symbols_exported_and_bound():
     for name in names:
         assert hasattr(L, name), f"{name} declared in include/mnk_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in mnk_b200/_lib.py"
-    assert L.mnk_version() == 100
+    assert L.mnk_version() == 200       # MNK_B200_VERSION of include/mnk_b200.h (round 2)
 
 
 def test_state_words():

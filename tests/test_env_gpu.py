@@ -265,6 +265,49 @@ def test_host_step_two_groups_in_flight():
         assert torch.equal(groups[g]._bits.view(2, -1, half), bits[:, :, g * half:(g + 1) * half])
 
 
+@pytest.mark.parametrize("slab,views,dtype", [(1, False, torch.long), (3, True, torch.long), (4, False, torch.int32),
+                                              (40, False, torch.long), (5, True, torch.int32)], ids=lambda v: str(v))
+def test_host_step_loop_matches_single_steps(slab, views, dtype):
+    """mnk_step_host_loop (K steps per C call, slab-pipelined copies) against K device-side single steps of a twin env:
+    rewards / dones bit-identical for every step, observation ring and host copies of the views identical, final
+    state identical -- for slab sizes that divide K, do not divide it, and exceed it."""
+    ne, K = 1500, 17
+    env, twin = make_env(9, 9, 5, ne), make_env(9, 9, 5, ne)
+    env.reset(), twin.reset()
+    for w in range(30):                                   # mid-game positions with finished games around
+        a = twin.random_legal_actions(3, w)
+        twin.step_autoreset(a, materialise=False), env.step_autoreset(a, materialise=False)
+    host_a = torch.empty((K, ne), dtype=dtype).pin_memory()
+    want = []
+    for s_ in range(K):
+        a = twin.random_legal_actions(4, s_)
+        host_a[s_].copy_(a)
+        o, r, d = twin.step_autoreset(a)
+        want.append((o["observation"].cpu(), o["action_mask"].cpu(), r.cpu(), d.cpu()))
+    host_out = torch.empty((K, 5 * ne), dtype=torch.uint8).pin_memory()
+    ring_n = max(2 * min(slab, K), 3)
+    ring = ([torch.empty((ne, 2, 9, 9), device=DEV) for _ in range(ring_n)],
+            [torch.empty((ne, 81), dtype=torch.bool, device=DEV) for _ in range(ring_n)])
+    host_obs = torch.empty((K, ne, 2, 9, 9)).pin_memory() if views else None
+    host_mask = torch.empty((K, ne, 81), dtype=torch.bool).pin_memory() if views else None
+    r_all, d_all = env.step_host_loop(host_a, host_out, slab_steps=slab, autoreset=True, ring=ring, host_obs=host_obs,
+                                      host_mask=host_mask)
+    assert r_all.shape == (K, ne) and d_all.shape == (K, ne) and not r_all.is_cuda
+    for s_ in range(K):
+        assert torch.equal(r_all[s_], want[s_][2]) and torch.equal(d_all[s_], want[s_][3]), s_
+        if views:
+            assert torch.equal(host_obs[s_], want[s_][0]) and torch.equal(host_mask[s_], want[s_][1]), s_
+    last = (K - 1) % ring_n
+    assert torch.equal(ring[0][last].cpu(), want[-1][0]) and torch.equal(ring[1][last].cpu(), want[-1][1])
+    assert env.state_checksum() == twin.state_checksum()
+    # packed mode (no views) continues from the same state
+    a = twin.random_legal_actions(5, 0)
+    host_a[0].copy_(a)
+    _, r, d = twin.step_autoreset(a, materialise=False)
+    r1, d1 = env.step_host_loop(host_a[:1], host_out, slab_steps=slab, autoreset=True)
+    assert torch.equal(r1[0], r.cpu()) and torch.equal(d1[0], d.cpu()) and env.state_checksum() == twin.state_checksum()
+
+
 def test_tournament_style_consumer_on_raw_env():
     """Second consumer of the env in the reference: MatchRunner._play_batch_games
     (src/model_comparison/match_runner.py:125-218) drives the RAW env -- reads env.current_player every

@@ -6,6 +6,8 @@ import torch
 import golden_io as gio
 from oracle import mnk_oracle as orc
 
+from mnk_b200 import RandomPolicy, TorchSelfPlayWrapper, TorchVectorMnkEnv
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
@@ -310,3 +312,45 @@ def test_play_batch_games_tournament_primitive():
     w, l, d = play_batch_games(RandomPolicy(9, seed=3), RandomPolicy(9, seed=4), (3, 3, 3), n, p1_is_black=False, device=DEV)
     assert abs(w / n - 0.288) < 0.012 and abs(l / n - 0.585) < 0.012 and abs(d / n - 0.127) < 0.01
     assert play_batch_games(None, None, (3, 3, 3), 0, True, device=DEV) == (0, 0, 0)
+
+
+def test_default_constructed_policies_draw_independently():
+    """Two policies built without a seed must not hand the same noise to consecutive plies: on
+    identical inputs their draws agree only as often as independent draws from the distribution would."""
+    rows, cells = 20000, 81
+    obs = {"observation": torch.zeros(rows, 2, 9, 9, device=DEV), "action_mask": torch.ones(rows, cells, dtype=torch.bool, device=DEV)}
+    a, b = RandomPolicy(cells), RandomPolicy(cells)
+    x, y = a.act(obs), b.act(obs)                       # both objects are at call count 1
+    agree = (x == y).float().mean().item()
+    assert abs(agree - 1.0 / cells) < 0.006, agree      # independent uniform draws agree with probability 1/81
+    same = RandomPolicy(cells, seed=9).act(obs), RandomPolicy(cells, seed=9).act(obs)
+    assert torch.equal(*same)                           # explicit equal seeds reproduce
+
+
+def test_random_legal_counter_is_64_bit():
+    """mnk_random_legal's counter is 64-bit end to end (r1: the kernel truncated it to 32 bits)."""
+    env = TorchVectorMnkEnv(9, 9, 5, 4096, device=DEV)
+    obs = env.reset()
+    mask = obs["action_mask"].cpu().numpy()
+    lo, hi = 12345, 12345 + (7 << 32)
+    a_lo, a_hi = env.random_legal_actions(seed=2, counter=lo), env.random_legal_actions(seed=2, counter=hi)
+    assert np.array_equal(a_lo.cpu().numpy(), orc.random_legal_actions(mask, 2, lo))
+    assert np.array_equal(a_hi.cpu().numpy(), orc.random_legal_actions(mask, 2, hi))
+    assert (a_lo != a_hi).float().mean().item() > 0.9
+
+
+def test_agent_side_is_a_live_writable_mirror():
+    """wrapper.agent_side (reference :13) can be written in place, as the reference's reset does with
+    ``self.agent_side[:] = ...`` (:23), and tracks the sides the kernels assign."""
+    env = TorchVectorMnkEnv(3, 3, 3, 64, device=DEV)
+    wr = TorchSelfPlayWrapper(env, seed=4)
+    wr.set_opponent(RandomPolicy(9, seed=1))
+    wr.reset(options={"agent_side": 0})
+    side = wr.agent_side
+    assert side.dtype == torch.long and int(side.sum()) == 0
+    side[:] = 1                                          # in-place write through the mirror
+    obs = wr.get_agent_obs()
+    raw = env.observe()
+    assert torch.equal(obs["observation"], raw["observation"].flip(1))       # canonical view now swaps the planes
+    wr.reset(options={"agent_side": torch.arange(64, device=DEV) % 2})
+    assert torch.equal(side, torch.arange(64, device=DEV) % 2)               # the held tensor follows
