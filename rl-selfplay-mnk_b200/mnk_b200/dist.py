@@ -101,3 +101,31 @@ def broadcast_module(module: torch.nn.Module, optimizer=None, src: int = 0, grou
                 for v in state.values():
                     if torch.is_tensor(v):
                         dist.broadcast(v, src=src, group=group)
+
+
+def pin_to_gpu_numa(local_rank: int):
+    """Best effort: restrict this process to the CPUs of the NUMA node the GPU hangs off (read from sysfs), so that the
+    host side of the per-slab copies and launches of mnk_step_host_loop does not cross sockets when 8 ranks share one
+    host.  Returns a short description, or None if nothing was changed."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node}: {len(allowed)} cpus"
+    except Exception:
+        return None
