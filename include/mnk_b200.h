@@ -249,18 +249,21 @@ int mnk_episode_stats(const float* rewards, const uint8_t* dones, int64_t num_en
  * ("resnet_b_s", configs.py:28-35), eval-mode BatchNorm folded: conv_in, `blocks` residual blocks and
  * the 1x1 convolutions that open the policy (32->2) and value (32->1) heads, as one tcgen05
  * implicit-GEMM kernel reading the packed bitboards (swap[e] != 0 exchanges the planes: the mover's /
- * agent's canonical view, as in mnk_observe).  bf16 operands, fp32 accumulation in TMEM.
- *   weights  bf16 [1+2*blocks][9 taps][4 k-chunks][32 c_out][8 c_in]  (tap = ky*3+kx; 16-byte aligned)
+ * agent's canonical view, as in mnk_observe).  16-bit floating-point operands ("op16": IEEE fp16 unless the
+ * library was built with -DMNK_ACT_BF16 -- see mnk_resnet_operand_dtype), fp32 accumulation in TMEM.
+ *   weights  op16 [1+2*blocks][9 taps][4 k-chunks][32 c_out][8 c_in]  (tap = ky*3+kx; 16-byte aligned)
  *   bias     f32  [1+2*blocks][32] (16-byte aligned)   head_w f32 [3][32], head_b f32 [3] (policy0, policy1, value)
  *   policy_feat f32 [num_envs][2*m*n]  (= Flatten(Conv2d(32,2,1)(features))), value_feat f32 [num_envs][m*n]
  *   error    NULL or int32[1], set to 1 if an internal barrier wait timed out (results invalid) */
+int mnk_resnet_operand_dtype(void);   /* 0 = IEEE fp16 (default build), 1 = bf16: element type of `weights` below */
+
 int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, const void* weights, const float* bias,
                      const float* head_w, const float* head_b, int32_t blocks, float* policy_feat,
                      float* value_feat, int32_t* error, void* stream);
 
 /* The same tower for boards with 3 <= m <= 10 rows (MNK_ERR_GEOM otherwise), with the three vertical taps fused
  * into the MMA's N dimension (csrc/mnk_resnet_rows.cu): identical arguments and results, except the weight layout
- *   weights_rows  bf16 [1+2*blocks][3 kx][4 k-chunks][ky*32 + c_out][8 c_in]   (16-byte aligned)
+ *   weights_rows  op16 [1+2*blocks][3 kx][4 k-chunks][ky*32 + c_out][8 c_in]   (16-byte aligned)
  * 2.1x fewer shared-memory operand reads per layer; the faster kernel wherever the board fits. */
 int mnk_resnet_tower_rows(const mnk_state_t* st, const uint8_t* swap, const void* weights_rows, const float* bias,
                           const float* head_w, const float* head_b, int32_t blocks, float* policy_feat,

@@ -30,7 +30,6 @@
 #include "mnk_dispatch.cuh"
 #include "mnk_umma.cuh"
 
-#include <cuda_bf16.h>
 
 namespace rn {
 constexpr int kC = 32;                        // tower channels
@@ -104,8 +103,9 @@ MNK_DEV void epilogue_row(Smem& sm, const u32* acc, const float (&bias)[NCH], in
             const u32 w[4] = {rsd.x, rsd.y, rsd.z, rsd.w};
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                v[kc * 8 + 2 * h] += __uint_as_float(w[h] << 16);
-                v[kc * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xFFFF0000u);
+                const float2 sk = act_unpack2(w[h]);
+                v[kc * 8 + 2 * h] += sk.x;
+                v[kc * 8 + 2 * h + 1] += sk.y;
             }
         }
     }
@@ -125,8 +125,7 @@ MNK_DEV void epilogue_row(Smem& sm, const u32* acc, const float (&bias)[NCH], in
             u32 w[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                const __nv_bfloat162 pr = __floats2bfloat162_rn(v[kc * 8 + 2 * h], v[kc * 8 + 2 * h + 1]);
-                w[h] = *reinterpret_cast<const u32*>(&pr) & keep;
+                w[h] = act_pack2(v[kc * 8 + 2 * h], v[kc * 8 + 2 * h + 1]) & keep;
             }
             *out_row[kc] = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -181,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 2) resnet_tower_kernel(Params p) {
         const u32 black = (u32)(wb >> (bit & 63)) & 1u, white = (u32)(ww >> (bit & 63)) & 1u;
         const u32 me = sw ? white : black, enemy = sw ? black : white;
         const int row = kMargin + s * p.rs + bit;
-        reinterpret_cast<uint4*>(&sm.act[0][0])[row] = make_uint4(me * 0x3F80u | (enemy * 0x3F80u) << 16, 0, 0, 0);
+        reinterpret_cast<uint4*>(&sm.act[0][0])[row] = make_uint4(me * kActOne | (enemy * kActOne) << 16, 0, 0, 0);
     }
     // which of this thread's 8 pixel rows (one per M-block) are real board cells: fixed for all layers
     const int quarter = warp & 3, half = (warp >> 2) & 1;
@@ -353,6 +352,8 @@ __global__ void __launch_bounds__(kThreads, 2) resnet_tower_kernel(Params p) {
     }
 }
 }  // namespace rn
+
+extern "C" int mnk_resnet_operand_dtype(void) { return mnk_umma::kActF16 ? 0 : 1; }
 
 extern "C" int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, const void* weights, const float* bias,
                                 const float* head_w, const float* head_b, int32_t blocks, float* policy_feat,

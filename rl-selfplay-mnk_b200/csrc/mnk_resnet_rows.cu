@@ -34,7 +34,6 @@
 #include "mnk_dispatch.cuh"
 #include "mnk_umma.cuh"
 
-#include <cuda_bf16.h>
 
 namespace rr {
 using namespace mnk_umma;
@@ -142,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
         const bool sw = p.swap != nullptr && p.swap[e] != 0;
         const u32 black = (u32)(wb >> (bit & 63)) & 1u, white = (u32)(ww >> (bit & 63)) & 1u;
         const u32 me = sw ? white : black, enemy = sw ? black : white;
-        act[kPad + r * 128 + s * p.pw + c] = make_uint4(me * 0x3F80u | (enemy * 0x3F80u) << 16, 0, 0, 0);
+        act[kPad + r * 128 + s * p.pw + c] = make_uint4(me * kActOne | (enemy * kActOne) << 16, 0, 0, 0);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -283,8 +282,9 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
                         const u32 w[4] = {rsd.x, rsd.y, rsd.z, rsd.w};
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
-                            v[kc * 8 + 2 * h] += __uint_as_float(w[h] << 16);
-                            v[kc * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xFFFF0000u);
+                            const float2 sk = act_unpack2(w[h]);
+                            v[kc * 8 + 2 * h] += sk.x;
+                            v[kc * 8 + 2 * h + 1] += sk.y;
                         }
                     }
                 }
@@ -297,8 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
                         u32 w[4];
 #pragma unroll
                         for (int h = 0; h < 4; ++h) {
-                            const __nv_bfloat162 pr = __floats2bfloat162_rn(v[kc * 8 + 2 * h], v[kc * 8 + 2 * h + 1]);
-                            w[h] = *reinterpret_cast<const u32*>(&pr) & keep;
+                            w[h] = act_pack2(v[kc * 8 + 2 * h], v[kc * 8 + 2 * h + 1]) & keep;
                         }
                         *out_row[kc] = make_uint4(w[0], w[1], w[2], w[3]);
                     }

@@ -124,6 +124,7 @@ SIGNATURES = {
     "mnk_rollout_gather": (_I32, [_I32, _I32, _I32, _VP, _I64, _VP, _I64, _VP, _VP, _VP]),
     "mnk_gae": (_I32, [_VP, _VP, _VP, _VP, _I64, _I64, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP]),
     "mnk_episode_stats": (_I32, [_VP, _VP, _I64, _VP, _VP, _VP, _VP]),
+    "mnk_resnet_operand_dtype": (_I32, []),
     "mnk_resnet_tower": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "mnk_resnet_tower_rows": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "mnk_resnet_heads": (_I32, [_VP, _VP, _I64, _I32, ctypes.POINTER(MnkHeadsWeights), _VP, _VP, _VP]),

@@ -30,22 +30,28 @@ def _fold(conv: nn.Conv2d, bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tens
     return w.float(), b.float()
 
 
+def operand_dtype() -> torch.dtype:
+    """Element type of the tower kernels' tensor-core operands as compiled into the library (fp16 by default; bf16
+    with -DMNK_ACT_BF16): the conv weights are laid out in it."""
+    return torch.float16 if _lib.lib().mnk_resnet_operand_dtype() == 0 else torch.bfloat16
+
+
 def _arrange(w: torch.Tensor) -> torch.Tensor:
-    """[c_out=32][c_in<=32][3][3] fp32 -> bf16 [tap][k-chunk=4][c_out][8 c_in] (zero-padded input channels)."""
+    """[c_out=32][c_in<=32][3][3] fp32 -> operand type [tap][k-chunk=4][c_out][8 c_in] (zero-padded input channels)."""
     c_out, c_in = w.shape[0], w.shape[1]
     full = torch.zeros((c_out, 32, 3, 3), dtype=torch.float32, device=w.device)
     full[:, :c_in] = w
     t = full.permute(2, 3, 1, 0).reshape(9, 4, 8, c_out)          # [tap][kc][j][c_out]
-    return t.permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)   # [tap][kc][c_out][j]
+    return t.permute(0, 1, 3, 2).contiguous().to(operand_dtype())   # [tap][kc][c_out][j]
 
 
 def _arrange_rows(w: torch.Tensor) -> torch.Tensor:
-    """Same parameters for the board-row kernel (mnk_resnet_tower_rows): bf16 [kx][k-chunk=4][ky*32 + c_out][8 c_in]."""
+    """Same parameters for the board-row kernel (mnk_resnet_tower_rows): operand type [kx][k-chunk=4][ky*32 + c_out][8 c_in]."""
     c_out, c_in = w.shape[0], w.shape[1]
     full = torch.zeros((c_out, 32, 3, 3), dtype=torch.float32, device=w.device)
     full[:, :c_in] = w
     t = full.permute(3, 1, 2, 0).reshape(3, 4, 8, 3, c_out)        # [kx][kc][j][ky][c_out]
-    return t.permute(0, 1, 3, 4, 2).reshape(3, 4, 3 * c_out, 8).contiguous().to(torch.bfloat16)
+    return t.permute(0, 1, 3, 4, 2).reshape(3, 4, 3 * c_out, 8).contiguous().to(operand_dtype())
 
 
 ROWS_KERNEL_BOARD_ROWS = (3, 10)      # mnk_resnet_tower_rows: boards with 3 <= m <= 10 rows (shared-memory bound)
@@ -75,27 +81,45 @@ class NativeResNet:
         self.blocks = len(model.res_blocks)
         folded = [_fold(c, b) for c, b in convs]
         dev = self._dev
-        self.weights = torch.stack([_arrange(w.to(dev)) for w, _ in folded]).contiguous()    # bf16 [L][9][4][32][8]
-        self.weights_rows = torch.stack([_arrange_rows(w.to(dev)) for w, _ in folded]).contiguous()   # bf16 [L][3][4][96][8]
-        self.bias = torch.stack([b.to(dev) for _, b in folded]).contiguous()                  # f32 [L][32]
-        pc, vc = model.policy_head[0], model.value_head[0]
-        self.head_w = torch.cat([pc.weight.reshape(2, 32), vc.weight.reshape(1, 32)]).float().to(dev).contiguous()
-        self.head_b = torch.cat([pc.bias.reshape(2), vc.bias.reshape(1)]).float().to(dev).contiguous()
-        self.policy_tail = nn.Sequential(*list(model.policy_head)[2:]).to(dev).eval()        # LN, ReLU, Linear, LN, ReLU, Linear
-        self.value_tail = nn.Sequential(*list(model.value_head)[2:]).to(dev).eval()          # ... + Tanh
-        self._err = torch.zeros(1, dtype=torch.int32, device=dev)
-        # fused heads kernel (mnk_resnet_heads): LN / Linear parameters, Linear weights transposed to [in][out]
         ph, vh = model.policy_head, model.value_head
+        pc, vc = ph[0], vh[0]
         if ph[4].out_features != 128 or vh[4].out_features != 128:
             raise ValueError("NativeResNet supports head_hidden_dim = 128 (resnet_b_s)")
         f = lambda t: t.detach().float().to(dev).contiguous()
-        self._head_tensors = {
+        fresh = {
+            "weights": torch.stack([_arrange(w.to(dev)) for w, _ in folded]).contiguous(),            # bf16 [L][9][4][32][8]
+            "weights_rows": torch.stack([_arrange_rows(w.to(dev)) for w, _ in folded]).contiguous(),  # bf16 [L][3][4][96][8]
+            "bias": torch.stack([b.to(dev) for _, b in folded]).contiguous(),                         # f32 [L][32]
+            "head_w": torch.cat([pc.weight.reshape(2, 32), vc.weight.reshape(1, 32)]).float().to(dev).contiguous(),
+            "head_b": torch.cat([pc.bias.reshape(2), vc.bias.reshape(1)]).float().to(dev).contiguous(),
+            # fused heads kernel (mnk_resnet_heads): LN / Linear parameters, Linear weights transposed to [in][out]
             "p_ln1_w": f(ph[2].weight), "p_ln1_b": f(ph[2].bias), "p_w1t": f(ph[4].weight.t()), "p_b1": f(ph[4].bias),
             "p_ln2_w": f(ph[5].weight), "p_ln2_b": f(ph[5].bias), "p_w2t": f(ph[7].weight.t()), "p_b2": f(ph[7].bias),
             "v_ln1_w": f(vh[2].weight), "v_ln1_b": f(vh[2].bias), "v_w1t": f(vh[4].weight.t()), "v_b1": f(vh[4].bias),
             "v_ln2_w": f(vh[5].weight), "v_ln2_b": f(vh[5].bias), "v_w2": f(vh[7].weight.reshape(-1)), "v_b2": f(vh[7].bias),
         }
-        self._heads = MnkHeadsWeights(*[self._head_tensors[n].data_ptr() for n in MnkHeadsWeights.NAMES])
+        # Device tensors live at STABLE addresses: a refresh copies into the existing storage, so raw pointers baked
+        # into a captured CUDA graph (RolloutCollector.collect(graph=True)) keep reading current weights.  A change of
+        # shape (another board size / block count) re-allocates and shows up in pointer_signature().
+        old = getattr(self, "_params", None)
+        if old is not None and all(old[k].shape == v.shape and old[k].dtype == v.dtype for k, v in fresh.items()):
+            for k, v in fresh.items():
+                old[k].copy_(v)
+        else:
+            self._params = fresh
+            self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        P = self._params
+        self.weights, self.weights_rows, self.bias = P["weights"], P["weights_rows"], P["bias"]
+        self.head_w, self.head_b = P["head_w"], P["head_b"]
+        self._head_tensors = {n: P[n] for n in MnkHeadsWeights.NAMES}
+        self._heads = MnkHeadsWeights(*[P[n].data_ptr() for n in MnkHeadsWeights.NAMES])
+        self.policy_tail = nn.Sequential(*list(ph)[2:]).to(dev).eval()        # LN, ReLU, Linear, LN, ReLU, Linear
+        self.value_tail = nn.Sequential(*list(vh)[2:]).to(dev).eval()          # ... + Tanh
+        self.version = getattr(self, "version", 0) + 1
+
+    def pointer_signature(self):
+        """Addresses of every device tensor a captured launch reads (see RolloutCollector._collect_graphed)."""
+        return tuple(t.data_ptr() for t in self._params.values()) + (self._err.data_ptr(),)
 
     @torch.no_grad()
     def tails(self, pf: torch.Tensor, vf: torch.Tensor, want_value: bool = True):

@@ -1,11 +1,12 @@
 """tcgen05 forward (mnk_resnet_tower + torch head tails) against the reference network's outputs.
 
 Tolerance (BASELINE.json: "policy logits must match within 1e-3 relative in bf16").  The kernel
-keeps activations in bf16 between layers (fp32 accumulation in TMEM, fp32 heads); the fixture is
-the reference network in fp32.  Asserted on the normalised masked logits: relative L2 error
-<= 1e-3 (measured on B200: 8.1e-4 at 9x9, 2.7e-4 at 13x13), max |delta| <= 5e-3 * max |logit|
-(measured 2.5e-3: single bf16-rounded outliers), -inf positions identical, and the kernel at
-least as close to the fp32 reference as stock PyTorch bf16 autocast of the same network."""
+keeps activations as 16-bit floats between layers (IEEE fp16 operands by default: same tensor-core rate as
+bf16, 8x finer rounding; fp32 accumulation in TMEM, fp32 heads); the fixture is the reference network in
+fp32.  Asserted on the normalised masked logits ELEMENT-WISE: max |delta| <= 1e-3 * max |logit|, relative L2
+error <= 3e-4, -inf positions identical, and the kernel closer to the fp32 reference than stock PyTorch bf16
+autocast of the same network.  (The bf16 build, -DMNK_ACT_BF16, measured 2.5e-3 / 8.1e-4 in round 1 and gets
+the looser bounds.)"""
 import numpy as np
 import pytest
 import torch
@@ -40,9 +41,11 @@ def test_native_forward_matches_reference(path):
     ac_err = np.abs(ac[fin] - want[fin]).max()
     print(f"{gio.name(path)}: max|d|={err.max():.3e} (scale {scale:.2f}) rel_l2={rel_l2:.3e} autocast max|d|={ac_err:.3e} "
           f"value max|d|={np.abs(value.cpu().numpy() - g['value']).max():.3e}")
-    assert rel_l2 <= 1e-3 and err.max() <= 5e-3 * scale
+    from mnk_b200.resnet import operand_dtype
+    f16 = operand_dtype() == torch.float16
+    assert rel_l2 <= (3e-4 if f16 else 1e-3) and err.max() <= (1e-3 if f16 else 5e-3) * scale
     assert err.max() <= ac_err
-    assert np.abs(value.cpu().numpy() - g["value"]).max() <= 3e-2
+    assert np.abs(value.cpu().numpy() - g["value"]).max() <= (4e-3 if f16 else 3e-2)
     # argmax agreement where the reference's top-2 gap exceeds the error bound
     top2 = np.sort(np.where(fin, want, -np.inf), axis=1)[:, -2:]
     clear = (top2[:, 1] - top2[:, 0]) > 2 * err.max()
@@ -90,6 +93,31 @@ def test_board_row_kernel_matches_tap_kernel_and_fp32_tower(m, n, k):
             rel = lambda x: float((x - want).norm() / (want.norm() + 1e-12))
             assert rel(got) <= 2e-2 and rel(got) <= 1.5 * rel(tap) + 1e-3, (ne, rel(got), rel(tap))   # bf16 activations, 9 layers
             assert float((got - want).abs().max()) <= 5e-2 * scale
+
+
+def test_refresh_keeps_device_addresses_and_takes_new_weights():
+    """NativeResNet.refresh copies into the existing device tensors (raw pointers baked into a captured rollout
+    graph stay valid and read the NEW weights); the result equals a freshly built NativeResNet."""
+    from mnk_b200 import NativeResNet, ResNetActorCritic, TorchVectorMnkEnv
+    torch.manual_seed(8)
+    net = ResNetActorCritic((2, 9, 9), 81).to(DEV).eval()
+    native = NativeResNet(net, device=DEV)
+    env = TorchVectorMnkEnv(9, 9, 5, 100, device=DEV)
+    env.reset()
+    for t in range(20):
+        env.step_autoreset(env.random_legal_actions(5, t), materialise=False)
+    before = native.forward_env(env)[0].clone()
+    sig = native.pointer_signature()
+    with torch.no_grad():
+        for prm in net.parameters():
+            prm.add_(0.02 * torch.randn_like(prm))
+    native.refresh(net)
+    assert native.pointer_signature() == sig
+    after, value = native.forward_env(env)
+    fresh = NativeResNet(net, device=DEV)
+    want, want_value = fresh.forward_env(env)
+    assert torch.equal(after, want) and torch.equal(value, want_value) and not torch.equal(after, before)
+    assert fresh.pointer_signature() != sig
 
 
 def test_native_forward_from_env_bitboards_and_batch_tails():
