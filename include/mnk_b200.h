@@ -269,6 +269,33 @@ int mnk_resnet_tower_rows(const mnk_state_t* st, const uint8_t* swap, const void
                           const float* head_w, const float* head_b, int32_t blocks, float* policy_feat,
                           float* value_feat, int32_t* error, void* stream);
 
+/* The same tower with TRAIN-MODE BatchNorm, as the reference's rollout forward runs it (src/alg/ppo.py:97 calls the
+ * network without .eval(); BatchNorm2d of src/alg/architectures/resnet.py:9-21,27-31): every layer normalises with the
+ * mean / biased variance of THIS batch over (envs, rows, columns) and updates running_mean / running_var in place
+ * (momentum, unbiased variance), exactly one conv layer per kernel launch (csrc/mnk_resnet_train.cu), 3 <= m <= 10.
+ *   weights_rows  op16 [1+2*blocks][3 kx][4 k-chunks][ky*32 + c_out][8 c_in]: the UNFOLDED conv weights
+ *   bn            per-layer BatchNorm parameters and statistics, f32 [1+2*blocks][32] each (layer 0 = conv_in, then
+ *                 conv1 / conv2 of every block); batch_stats (may be NULL) receives f32 [1+2*blocks][64]: the batch
+ *                 mean (conv bias included) and the biased batch variance of every layer
+ *   scratch       caller-owned device memory, 256-byte aligned, mnk_resnet_tower_train_scratch_bytes(...) bytes
+ *                 (fp16 pre-activation and op16 skip activations of the whole batch, ~24 KB per env at 9x9)
+ * Statistics are reduced in a fixed order: results are bit-reproducible for a given device and batch. */
+typedef struct mnk_bn_train {
+    const float* gamma;      /* BatchNorm2d.weight */
+    const float* beta;       /* BatchNorm2d.bias   */
+    const float* conv_bias;  /* Conv2d.bias (cancels in the normalised output; enters running_mean) */
+    float* running_mean;     /* updated in place */
+    float* running_var;      /* updated in place */
+    float* batch_stats;      /* NULL or f32 [layers][64] */
+    float momentum, eps;
+} mnk_bn_train_t;
+
+int64_t mnk_resnet_tower_train_scratch_bytes(int32_t m, int32_t n, int64_t num_envs, int32_t blocks);
+
+int mnk_resnet_tower_train(const mnk_state_t* st, const uint8_t* swap, const void* weights_rows, const mnk_bn_train_t* bn,
+                           const float* head_w, const float* head_b, int32_t blocks, void* scratch, int64_t scratch_bytes,
+                           float* policy_feat, float* value_feat, int32_t* error, void* stream);
+
 /* The heads' tails after the tower (resnet.py:41-63), one kernel, fp32:
  *   logits = Linear(128,A)(ReLU(LN(128)(Linear(2A,128)(ReLU(LN(2A)(policy_feat))))))
  *   values = Tanh(Linear(128,1)(ReLU(LN(128)(Linear(A,128)(ReLU(LN(A)(value_feat)))))))

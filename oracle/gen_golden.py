@@ -317,7 +317,33 @@ def gen_resnet(seed, m, n, k, batch):
     return out
 
 
+def gen_resnet_train(seed, m, n, k, batch):
+    """TRAIN-mode forward of the same network, as PPOAgent.learn's rollout runs it (src/alg/ppo.py:97: the module is
+    never switched to eval there): BatchNorm uses the statistics of this batch and updates its running buffers.
+    Records the parameters BEFORE the call, the outputs, and the running statistics AFTER it."""
+    import importlib
+    cfg = importlib.import_module("alg.architectures.configs")
+    base = gen_resnet(seed, m, n, k, batch)         # same randomised weights / positions as the eval fixture recipe
+    net = cfg.ResNetSActorCritic((2, m, n), m * n)
+    net.load_state_dict({key[len("param/"):]: torch.from_numpy(v) for key, v in base.items() if key.startswith("param/")})
+    net.train()
+    x = torch.from_numpy(np.unpackbits(base["obs"], axis=1)[:, :2 * m * n].reshape(batch, 2, m, n).astype(np.float32))
+    mask = torch.from_numpy(np.unpackbits(base["mask"], axis=1)[:, :m * n].astype(bool))
+    with torch.no_grad():
+        dist, value = net(x, mask)
+    out = {key: v for key, v in base.items() if key.startswith("param/") or key in ("geom", "obs", "mask")}
+    out.update(logits=dist.logits.numpy(), value=value.numpy())
+    for key, v in net.state_dict().items():
+        if "running_" in key or "num_batches" in key:
+            out[f"after/{key}"] = v.numpy()
+    return out
+
+
 def main():
+    if "--resnet-train-only" in sys.argv:
+        np.savez_compressed(os.path.join(OUT, "resnet_train_b_s_9x9.npz"), **gen_resnet_train(21, 9, 9, 5, 96))
+        np.savez_compressed(os.path.join(OUT, "resnet_train_b_s_7x7.npz"), **gen_resnet_train(22, 7, 7, 4, 40))
+        return
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     env_cfgs = [  # m, n, k, envs, steps
@@ -337,6 +363,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "rollout_buffer_gae.npz"), **gen_rollout_buffer(9))
     np.savez_compressed(os.path.join(OUT, "resnet_b_s_9x9.npz"), **gen_resnet(11, 9, 9, 5, 96))
     np.savez_compressed(os.path.join(OUT, "resnet_b_s_13x13.npz"), **gen_resnet(12, 13, 13, 5, 24))
+    np.savez_compressed(os.path.join(OUT, "resnet_train_b_s_9x9.npz"), **gen_resnet_train(21, 9, 9, 5, 96))
+    np.savez_compressed(os.path.join(OUT, "resnet_train_b_s_7x7.npz"), **gen_resnet_train(22, 7, 7, 4, 40))
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} fixtures, {total / 1024:.1f} KiB -> {os.path.normpath(OUT)}")
 

@@ -1,0 +1,562 @@
+// mnk_resnet_train.cu -- the residual tower with TRAIN-MODE BatchNorm (batch statistics), one conv layer per launch.
+//
+// Reference: the rollout forward of PPOAgent.learn runs the network in train mode (src/alg/ppo.py:97; the module is
+// never put in eval mode there), so every BatchNorm2d of src/alg/architectures/resnet.py:9-21,27-31 normalises with
+// the mean / biased variance of the CURRENT batch over (N, H, W) and updates running_mean / running_var (momentum
+// 0.1, unbiased variance).  Batch statistics of layer L need layer L of EVERY env before layer L+1 of any env can
+// start, so the nine layers cannot be fused into one kernel the way the eval-mode tower is (mnk_resnet_rows.cu):
+//
+//   launch L (0 <= L < layers), persistent, one CTA per SM, each CTA walks groups of E = 128 / (n+1) envs:
+//     * operand of the group: layer 0 decodes the bitboards; layer L > 0 receives the RAW conv output z_{L-1} of the
+//       previous launch (fp16, already in the UMMA operand layout) by four 1-D TMA bulk copies, prefetched one group
+//       ahead into the other half of a double buffer, and transforms it IN PLACE:
+//           a_{L-1} = ReLU(scale_{L-1} * z_{L-1} + shift_{L-1} [+ a_{L-3} for the second conv of a block])
+//       (guard / unused lanes -> 0).  Block inputs a_0, a_2, ... are also written to HBM: they are the skip operands
+//       two launches later;
+//     * the MMAs are those of the board-row kernel: M-block b = board row b of the group, 3 (kx) x 2 (k-step) MMAs of
+//       M = 128, N = 96 = (ky, c_out), K = 16 into a ring of five 96-column TMEM slots, a commit-watcher warp and
+//       hardware named barriers for the hand-overs (see mnk_resnet_rows.cu for why);
+//     * the epilogue thread of (row r, lane p) adds its three TMEM slices, accumulates per-channel sum / sum of
+//       squares over the valid lanes in registers and stores z_L as fp16 (16-byte, warp-coalesced).  The conv bias is
+//       left out: BatchNorm subtracts the batch mean, so it cancels (it only enters running_mean);
+//     * at the end every CTA writes its 64 partial sums; the LAST CTA to finish (a device counter) adds the partials
+//       of all CTAs in a fixed order in double -- deterministic for a given grid -- and produces scale_L / shift_L
+//       for the next launch plus the running-statistics update.  No separate reduction launch, no atomics on floats.
+//   last launch: elementwise a_last = ReLU(BN(z_last) + skip) and the two 1x1 head convolutions -> head features.
+//
+// HBM traffic per env at 9x9: 9 x (6 KB z written + 6 KB read) + 4 x (6 KB a written + 6 KB read) = 156 KB -- 0.8 ms
+// per 32,768 envs at the measured HBM peak, next to 0.6 ms of tensor-core time: this forward is bound by both.
+#include <algorithm>
+
+#include "mnk_dispatch.cuh"
+#include "mnk_umma.cuh"
+
+namespace rt {
+using namespace mnk_umma;
+constexpr int kC = 32;
+constexpr int kChunks = kC / 8;
+constexpr int kN = 3 * kC;
+constexpr int kMaxBoardRows = 10;
+constexpr int kMinBoardRows = 3;
+constexpr int kPad = 8;
+constexpr int kSlots = 5;
+constexpr int kTmemCols = 512;
+constexpr int kLead = 4;
+constexpr int kStepBarrier0 = 3;              // named barriers 3..7: "epilogue step e done" (id 3 + e % 5)
+constexpr int kTokenBarrier0 = 8;             // 8..12: "the blocks step e needs are committed"
+constexpr int kReadyBarrier = 13;             // "the operand of this group is in shared memory"
+constexpr int kLayerWeightBytes = 3 * kChunks * kN * 16;   // 18,432
+constexpr int kEpiSets = 2;
+constexpr int kSetWarps = 8;
+constexpr int kEpiWarps = kEpiSets * kSetWarps;
+constexpr int kEpiThreads = 32 * kEpiWarps;   // 512: also the transform's thread count (4 k-chunks x 128 lanes)
+constexpr int kMmaWarp = kEpiWarps;
+constexpr int kWatchWarp = kMmaWarp + 1;
+constexpr int kThreads = 32 * (kWatchWarp + 1);
+constexpr u32 kIdesc = umma_idesc_bf16(kN);
+constexpr int kRowBatch = 5;                  // transform: skip rows fetched per batch (registers)
+
+struct Smem {
+    alignas(128) unsigned char wts[kLayerWeightBytes];
+    alignas(16) float scale[kC];
+    float shift[kC];
+    float red[kEpiWarps][32];
+    alignas(8) unsigned long long mma_bar[kSlots];
+    unsigned long long wts_bar;
+    unsigned long long in_bar[2];
+    unsigned int tmem_base;
+    unsigned int is_last;
+    alignas(128) unsigned char act[1];        // [2 buffers][4 k-chunks][m*128 + 2*kPad rows][16 B]
+};
+
+struct Params {
+    int m, n, words, layer;
+    long long num_envs, groups;
+    int epc, pw;
+    const u64* bits;
+    const uint8_t* swap;
+    const unsigned char* z_in;        // fp16 [groups][4][m][128][8]
+    const unsigned char* skip_in;     // op16, same layout, or null
+    unsigned char* a_out;             // op16, same layout, or null
+    unsigned char* z_out;             // fp16
+    const unsigned char* weights;     // this layer: op16 [3][4][96][8], unfolded conv weights
+    const float* in_scale_shift;      // f32 [64] of layer L-1
+    float* partials;                  // f32 [grid][64]
+    const float* gamma;               // this layer's BatchNorm weight / bias, conv bias, running statistics: f32 [32] each
+    const float* beta;
+    const float* conv_bias;
+    float* running_mean;
+    float* running_var;
+    float* out_scale_shift;           // f32 [64] of layer L
+    float* batch_stats;               // null or f32 [64]: batch mean (conv bias included), biased variance
+    unsigned int* counter;
+    float momentum, eps;
+    double count;                     // num_envs * m * n
+    int* error;
+};
+
+MNK_DEV void stg128(void* ptr, uint4 v) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+MNK_DEV uint4 ldg128(const void* ptr) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+    return v;
+}
+MNK_DEV void l2_prefetch(const void* ptr, u32 bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+MNK_DEV float2 half2_to_float2(u32 w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+MNK_DEV u32 float2_to_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const u32*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m = p.m, cells = p.m * p.n;
+    const int plane16 = m * 128 + 2 * kPad;                  // rows (16-byte units) per k-chunk plane
+    const int buf16 = kChunks * plane16;                     // 16-byte units per operand buffer
+    uint4* const act = reinterpret_cast<uint4*>(&sm.act[0]);
+    const bool first = p.layer == 0;
+    const int my_groups = (int)((p.groups - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const size_t plane_bytes = (size_t)m * 128 * 16;
+    const size_t group_bytes = kChunks * plane_bytes;
+    const int total_steps = my_groups * m;
+    const int lead = min(kLead, m);
+
+    // ---- one-time setup -----------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int i = 0; i < kSlots; ++i) mbar_init(&sm.mma_bar[i], 1);
+        mbar_init(&sm.wts_bar, 1);
+        mbar_init(&sm.in_bar[0], 1);
+        mbar_init(&sm.in_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&sm.wts_bar, kLayerWeightBytes);
+        tma_bulk_g2s(&sm.wts[0], p.weights, kLayerWeightBytes, &sm.wts_bar);
+        if (!first) {   // z of this CTA's first group
+            const unsigned char* src = p.z_in + (size_t)blockIdx.x * group_bytes;
+            mbar_expect_tx(&sm.in_bar[0], (u32)group_bytes);
+            for (int c = 0; c < kChunks; ++c)
+                tma_bulk_g2s(act + c * plane16 + kPad, src + c * plane_bytes, (u32)plane_bytes, &sm.in_bar[0]);
+        }
+    }
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    {
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        if (first) {   // k-chunks 0-1 of both buffers (the decode sets the stones of chunk 0; chunk 1 stays zero)
+            for (int i = tid; i < 2 * 2 * plane16; i += kThreads) act[(i / (2 * plane16)) * buf16 + i % (2 * plane16)] = zero;
+        } else {       // the pad rows of all eight planes (the bulk copies fill rows kPad .. kPad + m*128)
+            for (int i = tid; i < 2 * kChunks * 2 * kPad; i += kThreads) {
+                const int plane = i / (2 * kPad), r = i % (2 * kPad);
+                act[plane * plane16 + (r < kPad ? r : m * 128 + r)] = zero;
+            }
+            if (tid < 2 * kC) (&sm.scale[0])[tid] = p.in_scale_shift[tid];     // scale[32] then shift[32]
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const u32 tmem_base = sm.tmem_base;
+    bool ok = true;
+
+    if (warp == kMmaWarp) {
+        // ================= MMA issue (one elected lane) + prefetch of the next group's operand ====================
+        ok = __all_sync(MNK_FULL_WARP, mbar_wait(&sm.wts_bar, 0)) != 0;
+        const u64 b_d0 = umma_desc(smem_u32(&sm.wts[0]), kN * 16, 128);
+        const u32 b_lo0 = (u32)b_d0, b_hi = (u32)(b_d0 >> 32);
+        const u32 act_lo = smem_u32(&sm.act[0]) + kPad * 16;
+        int g = 0;
+        for (int i = 0; i < my_groups; ++i) {
+            const int buf = i & 1;
+            // operand of group i transformed; every epilogue warp has also left group i-1, so the other buffer is free
+            asm volatile("bar.sync %0, %1;" ::"r"(kReadyBarrier), "r"(kEpiThreads + 32) : "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (!first && i + 1 < my_groups && elect_one()) {
+                const size_t goff = ((size_t)blockIdx.x + (size_t)(i + 1) * gridDim.x) * group_bytes;
+                uint4* dst = act + (buf ^ 1) * buf16 + kPad;
+                mbar_expect_tx(&sm.in_bar[buf ^ 1], (u32)group_bytes);
+                for (int c = 0; c < kChunks; ++c)
+                    tma_bulk_g2s(dst + c * plane16, p.z_in + goff + c * plane_bytes, (u32)plane_bytes, &sm.in_bar[buf ^ 1]);
+                if (p.skip_in != nullptr)
+                    for (int c = 0; c < kChunks; ++c) l2_prefetch(p.skip_in + goff + c * plane_bytes, (u32)plane_bytes);
+            }
+            __syncwarp();
+            const u64 a_d0 = umma_desc(act_lo + (u32)(buf * buf16) * 16, (u32)plane16 * 16, 128);
+            const u32 a_lo0 = (u32)a_d0, a_hi = (u32)(a_d0 >> 32);
+            for (int b = 0; b < m; ++b, ++g) {
+                if (g >= lead)   // TMEM slot free: steps g-6 .. g-4 read Q_{g-5}
+                    asm volatile("bar.sync %0, %1;" ::"r"(kStepBarrier0 + (g - lead) % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int slot = g % kSlots;
+                const u32 d_tmem = tmem_base + (u32)(slot * kN);
+                const u32 a_row = a_lo0 + (u32)(b * 128 - 1);            // kx = 0 reads lane p-1
+                if (elect_one()) {
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            if (ks == 0 || !first)   // the input layer has 2 real channels: one K = 16 step
+                                umma_bf16_lohi(d_tmem, a_row + (u32)kx + (u32)(2 * ks) * (u32)plane16, a_hi,
+                                               b_lo0 + (u32)((kx * kChunks + 2 * ks) * kN), b_hi, kIdesc, (kx | ks) != 0);
+                        }
+                    }
+                    umma_commit(&sm.mma_bar[slot]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == kWatchWarp) {
+        // ================= commit watcher: MMA commits (mbarriers) -> named-barrier tokens, in step order ==========
+        for (int e = 0; e < total_steps; ++e) {
+            const int r = e % m;
+            const int need = (r < m - 1) ? e + 1 : e;
+            ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[need % kSlots], (u32)(need / kSlots) & 1u)) != 0;
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.arrive %0, %1;" ::"r"(kTokenBarrier0 + e % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");
+        }
+    } else {
+        // ================= transform (all 16 warps) + epilogue (two sets on alternate steps) =======================
+        const int t_chunk = tid >> 7, t_pos = tid & 127;                 // transform: k-chunk and lane of this thread
+        const int t_s = t_pos / p.pw, t_c = t_pos - t_s * p.pw;
+        const int quarter = warp & 3, half = (warp >> 2) & 1, set = warp / kSetWarps;
+        const int pos = quarter * 32 + lane;                             // epilogue: TMEM lane
+        const int e_s = pos / p.pw, e_c = pos - e_s * p.pw;
+        const u32 t_lane = tmem_base + ((u32)(quarter * 32) << 16) + (u32)(16 * half);
+        float s1[16], s2[16];
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) s1[ch] = s2[ch] = 0.0f;
+        int e = set;
+        int col = (set % kSlots) * kN;
+        int bar = set % kSlots;
+        for (int i = 0; i < my_groups; ++i) {
+            const long long G = (long long)blockIdx.x + (long long)i * gridDim.x;
+            const long long env0 = G * p.epc;
+            const int envs_here = (int)min((long long)p.epc, p.num_envs - env0);
+            const int buf = i & 1;
+            // ---- operand of group i ----------------------------------------------------------------------
+            if (first) {
+                uint4* plane = act + buf * buf16 + kPad;
+                for (int idx = tid; idx < p.epc * cells; idx += kEpiThreads) {
+                    const int s = idx / cells, cell = idx - s * cells;
+                    const int r = cell / p.n, c = cell - r * p.n, bit = cell + r;
+                    u32 word = 0;
+                    if (s < envs_here) {
+                        const long long en = env0 + s;
+                        const u64 wb = p.bits[(size_t)(bit >> 6) * p.num_envs + en];
+                        const u64 ww = p.bits[(size_t)(p.words + (bit >> 6)) * p.num_envs + en];
+                        const bool sw = p.swap != nullptr && p.swap[en] != 0;
+                        const u32 black = (u32)(wb >> (bit & 63)) & 1u, white = (u32)(ww >> (bit & 63)) & 1u;
+                        const u32 me = sw ? white : black, enemy = sw ? black : white;
+                        word = me * kActOne | (enemy * kActOne) << 16;
+                    }
+                    plane[r * 128 + s * p.pw + c] = make_uint4(word, 0, 0, 0);
+                }
+            } else {
+                ok = mbar_wait(&sm.in_bar[buf], (u32)(i >> 1) & 1u) && ok;
+                const bool valid = t_s < envs_here && t_c < p.n;
+                float sc[8], sh[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    sc[j] = valid ? sm.scale[t_chunk * 8 + j] : 0.0f;      // guard / unused lanes: ReLU(0 * z + 0) = 0 ...
+                    sh[j] = valid ? sm.shift[t_chunk * 8 + j] : 0.0f;
+                }
+                const u32 keep = valid ? 0xFFFFFFFFu : 0u;                 // ... and the skip operand is masked too
+                uint4* plane = act + buf * buf16 + t_chunk * plane16 + kPad + t_pos;
+                const size_t goff = (size_t)G * group_bytes + (size_t)t_chunk * plane_bytes + (size_t)t_pos * 16;
+                for (int r0 = 0; r0 < m; r0 += kRowBatch) {
+                    uint4 sk[kRowBatch];
+                    if (p.skip_in != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < kRowBatch; ++j)
+                            if (r0 + j < m) sk[j] = ldg128(p.skip_in + goff + (size_t)(r0 + j) * 2048);
+                    }
+#pragma unroll
+                    for (int j = 0; j < kRowBatch; ++j) {
+                        if (r0 + j < m) {
+                            const uint4 zq = plane[(r0 + j) * 128];
+                            const u32 zw[4] = {zq.x, zq.y, zq.z, zq.w};
+                            u32 ow[4];
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const float2 z2 = half2_to_float2(zw[h]);
+                                float y0 = fmaf(z2.x, sc[2 * h], sh[2 * h]);
+                                float y1 = fmaf(z2.y, sc[2 * h + 1], sh[2 * h + 1]);
+                                if (p.skip_in != nullptr) {
+                                    const u32 sw4[4] = {sk[j].x, sk[j].y, sk[j].z, sk[j].w};
+                                    const float2 k2 = act_unpack2(sw4[h] & keep);
+                                    y0 += k2.x;
+                                    y1 += k2.y;
+                                }
+                                ow[h] = act_pack2(fmaxf(y0, 0.0f), fmaxf(y1, 0.0f));
+                            }
+                            const uint4 out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                            plane[(r0 + j) * 128] = out;
+                            if (p.a_out != nullptr) stg128(p.a_out + goff + (size_t)(r0 + j) * 2048, out);
+                        }
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.arrive %0, %1;" ::"r"(kReadyBarrier), "r"(kEpiThreads + 32) : "memory");
+            // ---- this set's epilogue steps of group i --------------------------------------------------
+            const bool e_valid = e_s < envs_here && e_c < p.n;
+            unsigned char* zrow = p.z_out + (size_t)G * group_bytes + (size_t)(2 * half) * plane_bytes + (size_t)pos * 16;
+            const int e_end = (i + 1) * m;
+            while (e < e_end) {
+                const int r = e - i * m;
+                asm volatile("bar.sync %0, %1;" ::"r"(kTokenBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const bool up = r > 0, down = r < m - 1;
+                const int col_up = up ? (col == 0 ? (kSlots - 1) * kN : col - kN) : col;
+                const int col_down = down ? (col == (kSlots - 1) * kN ? 0 : col + kN) : col;
+                u32 q0[16], q1[16], q2[16];
+                tmem_ld16_issue(t_lane + (u32)col_up, q0);
+                tmem_ld16_issue(t_lane + (u32)(col + kC), q1);
+                tmem_ld16_issue(t_lane + (u32)(col_down + 2 * kC), q2);
+                tmem_ld_wait(q0);
+                tmem_ld_wait(q1);
+                tmem_ld_wait(q2);
+                float v[16];
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch) {
+                    float a = __uint_as_float(q1[ch]);
+                    if (up) a += __uint_as_float(q0[ch]);
+                    if (down) a += __uint_as_float(q2[ch]);
+                    v[ch] = e_valid ? a : 0.0f;
+                    s1[ch] += v[ch];
+                    s2[ch] = fmaf(v[ch], v[ch], s2[ch]);
+                }
+#pragma unroll
+                for (int kc = 0; kc < 2; ++kc) {
+                    u32 w[4];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) w[h] = float2_to_half2(v[kc * 8 + 2 * h], v[kc * 8 + 2 * h + 1]);
+                    stg128(zrow + (size_t)kc * plane_bytes + (size_t)r * 2048, make_uint4(w[0], w[1], w[2], w[3]));
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (e + lead < total_steps)
+                    asm volatile("bar.arrive %0, %1;" ::"r"(kStepBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
+                e += kEpiSets;
+                col += kEpiSets * kN;
+                if (col >= kSlots * kN) col -= kSlots * kN;
+                bar += kEpiSets;
+                if (bar >= kSlots) bar -= kSlots;
+            }
+        }
+        // per-warp sums of this warp's 16 channels over its 32 lanes
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                s1[ch] += __shfl_xor_sync(MNK_FULL_WARP, s1[ch], off);
+                s2[ch] += __shfl_xor_sync(MNK_FULL_WARP, s2[ch], off);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int ch = 0; ch < 16; ++ch) {
+                sm.red[warp][ch] = s1[ch];
+                sm.red[warp][16 + ch] = s2[ch];
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!ok && p.error != nullptr) atomicExch(p.error, 1);
+    if (warp == kMmaWarp) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+    // ---- batch statistics: this CTA's partial sums; the last CTA reduces all of them in a fixed order ----------
+    if (tid < 64) {
+        const int which = tid >> 5, ch = tid & 31, half = ch >> 4;
+        float acc = 0.0f;
+        for (int w = 0; w < kEpiWarps; ++w)
+            if (((w >> 2) & 1) == half) acc += sm.red[w][which * 16 + (ch & 15)];
+        p.partials[(size_t)blockIdx.x * 64 + tid] = acc;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(p.counter, 1u);
+        sm.is_last = (prev == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (sm.is_last != 0u && tid < kC) {
+        __threadfence();
+        double sum = 0.0, sq = 0.0;
+        for (unsigned int c = 0; c < gridDim.x; ++c) {
+            sum += (double)__ldcg(p.partials + (size_t)c * 64 + tid);
+            sq += (double)__ldcg(p.partials + (size_t)c * 64 + 32 + tid);
+        }
+        const double mean = sum / p.count;
+        const double var = fmax(sq / p.count - mean * mean, 0.0);
+        const float scale = (float)((double)p.gamma[tid] / sqrt(var + (double)p.eps));
+        p.out_scale_shift[tid] = scale;
+        p.out_scale_shift[32 + tid] = (float)((double)p.beta[tid] - mean * (double)scale);
+        const float mean_x = (float)(mean + (double)p.conv_bias[tid]);       // the conv bias was left out of z
+        const double unbiased = p.count > 1.0 ? var * p.count / (p.count - 1.0) : var;
+        p.running_mean[tid] = (1.0f - p.momentum) * p.running_mean[tid] + p.momentum * mean_x;
+        p.running_var[tid] = (1.0f - p.momentum) * p.running_var[tid] + p.momentum * (float)unbiased;
+        if (p.batch_stats != nullptr) {
+            p.batch_stats[tid] = mean_x;
+            p.batch_stats[32 + tid] = (float)var;
+        }
+        if (tid == 0) *p.counter = 0u;
+    }
+}
+
+// a_last = ReLU(BN(z_last) [+ skip]) and the 1x1 convolutions that open the two heads; one thread per (group, row, lane)
+struct FeatParams {
+    int m, n, epc, pw;
+    long long num_envs, groups;
+    const unsigned char* z_in;
+    const unsigned char* skip_in;
+    const float* scale_shift;
+    const float* head_w;     // f32 [3][32]
+    const float* head_b;     // f32 [3]
+    float* policy_feat;
+    float* value_feat;
+};
+
+__global__ void __launch_bounds__(256) resnet_train_features_kernel(FeatParams p) {
+    __shared__ float ss[64], hw[96], hb[3];
+    if (threadIdx.x < 64) ss[threadIdx.x] = p.scale_shift[threadIdx.x];
+    if (threadIdx.x < 96) hw[threadIdx.x] = p.head_w[threadIdx.x];
+    if (threadIdx.x < 3) hb[threadIdx.x] = p.head_b[threadIdx.x];
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per_group = (long long)p.m * 128;
+    if (idx >= p.groups * per_group) return;
+    const long long G = idx / per_group;
+    const int rp = (int)(idx - G * per_group), r = rp >> 7, pos = rp & 127;
+    const int s = pos / p.pw, c = pos - s * p.pw;
+    const long long env = G * p.epc + s;
+    if (s >= p.epc || c >= p.n || env >= p.num_envs) return;
+    const size_t plane_bytes = (size_t)p.m * 2048;
+    const size_t off = (size_t)G * kChunks * plane_bytes + (size_t)rp * 16;
+    float h0 = hb[0], h1 = hb[1], h2 = hb[2];
+#pragma unroll
+    for (int kc = 0; kc < kChunks; ++kc) {
+        const uint4 zq = ldg128(p.z_in + off + kc * plane_bytes);
+        uint4 sq = make_uint4(0, 0, 0, 0);
+        if (p.skip_in != nullptr) sq = ldg128(p.skip_in + off + kc * plane_bytes);
+        const u32 zw[4] = {zq.x, zq.y, zq.z, zq.w}, sw[4] = {sq.x, sq.y, sq.z, sq.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const float2 z2 = half2_to_float2(zw[h]);
+            const int ch = kc * 8 + 2 * h;
+            float y0 = fmaf(z2.x, ss[ch], ss[32 + ch]), y1 = fmaf(z2.y, ss[ch + 1], ss[32 + ch + 1]);
+            if (p.skip_in != nullptr) {
+                const float2 k2 = act_unpack2(sw[h]);
+                y0 += k2.x;
+                y1 += k2.y;
+            }
+            y0 = fmaxf(y0, 0.0f);
+            y1 = fmaxf(y1, 0.0f);
+            h0 = fmaf(y0, hw[ch], fmaf(y1, hw[ch + 1], h0));
+            h1 = fmaf(y0, hw[32 + ch], fmaf(y1, hw[32 + ch + 1], h1));
+            h2 = fmaf(y0, hw[64 + ch], fmaf(y1, hw[64 + ch + 1], h2));
+        }
+    }
+    const int cells = p.m * p.n, cell = r * p.n + c;
+    p.policy_feat[(size_t)env * 2 * cells + cell] = h0;
+    p.policy_feat[(size_t)env * 2 * cells + cells + cell] = h1;
+    p.value_feat[(size_t)env * cells + cell] = h2;
+}
+
+struct Layout {
+    size_t act_bytes;       // one activation array: groups * 4 * m * 128 * 16
+    size_t z[2], a[2], partials, scale_shift, counter, total;
+    long long groups;
+    int grid;
+};
+
+static inline Layout layout_for(int m, int n, long long num_envs, int layers) {
+    Layout l;
+    const int epc = 128 / (n + 1);
+    l.groups = (num_envs + epc - 1) / epc;
+    l.grid = (int)std::min<long long>(std::max<long long>(l.groups, 1), mnk_sm_count());
+    l.act_bytes = (size_t)l.groups * kChunks * m * 128 * 16;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t at = off; off += (bytes + 255) & ~(size_t)255; return at; };
+    l.z[0] = take(l.act_bytes); l.z[1] = take(l.act_bytes);
+    l.a[0] = take(l.act_bytes); l.a[1] = take(l.act_bytes);
+    l.partials = take((size_t)l.grid * 64 * sizeof(float));
+    l.scale_shift = take((size_t)layers * 64 * sizeof(float));
+    l.counter = take(256);
+    l.total = off;
+    return l;
+}
+}  // namespace rt
+
+extern "C" int64_t mnk_resnet_tower_train_scratch_bytes(int32_t m, int32_t n, int64_t num_envs, int32_t blocks) {
+    if (m < rt::kMinBoardRows || m > rt::kMaxBoardRows || n < 1 || n > 32 || num_envs < 0 || blocks < 0 || blocks > 8) return MNK_ERR_GEOM;
+    return (int64_t)rt::layout_for(m, n, num_envs, 1 + 2 * blocks).total;
+}
+
+extern "C" int mnk_resnet_tower_train(const mnk_state_t* st, const uint8_t* swap, const void* weights_rows, const mnk_bn_train_t* bn,
+                                      const float* head_w, const float* head_b, int32_t blocks, void* scratch, int64_t scratch_bytes,
+                                      float* policy_feat, float* value_feat, int32_t* error, void* stream) {
+    if (int rc = mnk_check_state(st)) return rc;
+    if (!weights_rows || !bn || !head_w || !head_b || !policy_feat || !value_feat || !scratch) return MNK_ERR_NULL;
+    if (!bn->gamma || !bn->beta || !bn->conv_bias || !bn->running_mean || !bn->running_var) return MNK_ERR_NULL;
+    if (blocks < 0 || blocks > 8) return MNK_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(weights_rows) & 15u) || (reinterpret_cast<uintptr_t>(scratch) & 255u)) return MNK_ERR_ALIGN;
+    if (st->m < rt::kMinBoardRows || st->m > rt::kMaxBoardRows) return MNK_ERR_GEOM;
+    if (st->num_envs == 0) return MNK_OK;
+    const int layers = 1 + 2 * blocks;
+    const rt::Layout lay = rt::layout_for(st->m, st->n, st->num_envs, layers);
+    if (scratch_bytes < (int64_t)lay.total) return MNK_ERR_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned char* base = static_cast<unsigned char*>(scratch);
+    float* scale_shift = reinterpret_cast<float*>(base + lay.scale_shift);
+    cudaError_t e = cudaMemsetAsync(base + lay.counter, 0, 256, s);
+    if (e != cudaSuccess) return (int)e;
+    const size_t smem = sizeof(rt::Smem) + 128 + (size_t)2 * rt::kChunks * (st->m * 128 + 2 * rt::kPad) * 16;
+    static std::atomic<size_t> granted[kMaxDevices];
+    if (int rc = mnk_optin_smem(rt::resnet_layer_train_kernel, smem, granted)) return rc;
+    for (int L = 0; L < layers; ++L) {
+        rt::Params p;
+        p.m = st->m; p.n = st->n; p.words = st->words; p.layer = L;
+        p.num_envs = st->num_envs; p.groups = lay.groups;
+        p.pw = st->n + 1; p.epc = 128 / p.pw;
+        p.bits = reinterpret_cast<const u64*>(st->bits); p.swap = swap;
+        const int in = L - 1;                                  // the operand of this launch is a_in
+        p.z_in = L > 0 ? base + lay.z[in & 1] : nullptr;
+        p.skip_in = (L > 0 && in >= 2 && (in & 1) == 0) ? base + lay.a[((in - 2) / 2) & 1] : nullptr;
+        p.a_out = (L > 0 && (in & 1) == 0 && in + 2 < layers) ? base + lay.a[(in / 2) & 1] : nullptr;
+        p.z_out = base + lay.z[L & 1];
+        p.weights = static_cast<const unsigned char*>(weights_rows) + (size_t)L * rt::kLayerWeightBytes;
+        p.in_scale_shift = L > 0 ? scale_shift + (size_t)in * 64 : nullptr;
+        p.partials = reinterpret_cast<float*>(base + lay.partials);
+        p.gamma = bn->gamma + L * 32; p.beta = bn->beta + L * 32; p.conv_bias = bn->conv_bias + L * 32;
+        p.running_mean = bn->running_mean + L * 32; p.running_var = bn->running_var + L * 32;
+        p.out_scale_shift = scale_shift + (size_t)L * 64;
+        p.batch_stats = bn->batch_stats ? bn->batch_stats + L * 64 : nullptr;
+        p.counter = reinterpret_cast<unsigned int*>(base + lay.counter);
+        p.momentum = bn->momentum; p.eps = bn->eps;
+        p.count = (double)st->num_envs * st->m * st->n;
+        p.error = error;
+        rt::resnet_layer_train_kernel<<<lay.grid, rt::kThreads, smem, s>>>(p);
+        if (int rc = mnk_launch_status()) return rc;
+    }
+    rt::FeatParams f;
+    const int last = layers - 1;
+    f.m = st->m; f.n = st->n; f.pw = st->n + 1; f.epc = 128 / f.pw;
+    f.num_envs = st->num_envs; f.groups = lay.groups;
+    f.z_in = base + lay.z[last & 1];
+    f.skip_in = (last >= 2 && (last & 1) == 0) ? base + lay.a[((last - 2) / 2) & 1] : nullptr;
+    f.scale_shift = scale_shift + (size_t)last * 64;
+    f.head_w = head_w; f.head_b = head_b; f.policy_feat = policy_feat; f.value_feat = value_feat;
+    const long long threads = lay.groups * st->m * 128;
+    rt::resnet_train_features_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(f);
+    return mnk_launch_status();
+}

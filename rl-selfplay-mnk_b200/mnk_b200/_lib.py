@@ -53,6 +53,13 @@ class MnkHeadsWeights(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in NAMES]
 
 
+class MnkBnTrain(ctypes.Structure):
+    """mnk_bn_train_t: per-layer BatchNorm parameters / statistics of the train-mode tower (f32 [layers][32] each)."""
+    _fields_ = [("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p), ("conv_bias", ctypes.c_void_p),
+                ("running_mean", ctypes.c_void_p), ("running_var", ctypes.c_void_p), ("batch_stats", ctypes.c_void_p),
+                ("momentum", ctypes.c_float), ("eps", ctypes.c_float)]
+
+
 SP_ACTIONS_I32, SP_RESET_ALL, SP_DETERMINISTIC_OPP = 1, 2, 4
 
 
@@ -127,6 +134,8 @@ SIGNATURES = {
     "mnk_resnet_operand_dtype": (_I32, []),
     "mnk_resnet_tower": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "mnk_resnet_tower_rows": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
+    "mnk_resnet_tower_train_scratch_bytes": (_I64, [_I32, _I32, _I64, _I32]),
+    "mnk_resnet_tower_train": (_I32, [_ST, _VP, _VP, ctypes.POINTER(MnkBnTrain), _VP, _VP, _I32, _VP, _I64, _VP, _VP, _VP, _VP]),
     "mnk_resnet_heads": (_I32, [_VP, _VP, _I64, _I32, ctypes.POINTER(MnkHeadsWeights), _VP, _VP, _VP]),
 }
 

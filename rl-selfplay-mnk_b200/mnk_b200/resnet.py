@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import MnkHeadsWeights, MnkState, check
+from ._lib import MnkBnTrain, MnkHeadsWeights, MnkState, check
 from .policy import Policy
 from .sampling import MaskedCategorical, fresh_seed, masked_sample
 
@@ -58,7 +58,17 @@ ROWS_KERNEL_BOARD_ROWS = (3, 10)      # mnk_resnet_tower_rows: boards with 3 <= 
 
 
 class NativeResNet:
-    def __init__(self, model: nn.Module, device="cuda", torch_heads: bool = False):
+    """bn_mode="eval": BatchNorm folded with the running statistics (NNPolicy / the frozen opponent / evaluation).
+    bn_mode="train": BatchNorm with the statistics of the CURRENT batch and running-statistics updates on the device
+    copies -- what the reference's rollout forward does (src/alg/ppo.py:97 never leaves train mode); one tcgen05
+    launch per layer (mnk_resnet_tower_train).  `export_running_stats(model)` writes the statistics back."""
+
+    def __init__(self, model: nn.Module, device="cuda", torch_heads: bool = False, bn_mode: str = "eval"):
+        if bn_mode not in ("eval", "train"):
+            raise ValueError("bn_mode must be 'eval' or 'train'")
+        self.bn_mode = bn_mode
+        self.train_forwards = 0             # train-mode forwards since the last export_running_stats
+        self._scratch = None
         self.torch_heads = torch_heads      # run the head tails through the original torch modules (debug / comparison)
         self.use_rows_kernel = True         # board-row tower kernel where the board fits it (m <= 10); False = tap kernel
         dev = torch.device(device)
@@ -98,6 +108,19 @@ class NativeResNet:
             "v_ln1_w": f(vh[2].weight), "v_ln1_b": f(vh[2].bias), "v_w1t": f(vh[4].weight.t()), "v_b1": f(vh[4].bias),
             "v_ln2_w": f(vh[5].weight), "v_ln2_b": f(vh[5].bias), "v_w2": f(vh[7].weight.reshape(-1)), "v_b2": f(vh[7].bias),
         }
+        if self.bn_mode == "train":          # unfolded conv weights + BatchNorm parameters / running statistics, [L][32]
+            bns = [b for _, b in convs]
+            if any(b.momentum != bns[0].momentum or b.eps != bns[0].eps or not b.track_running_stats for b in bns):
+                raise ValueError("NativeResNet(bn_mode='train') needs one momentum / eps and tracked running statistics")
+            self._bn_momentum, self._bn_eps = float(bns[0].momentum), float(bns[0].eps)
+            fresh.update({
+                "raw_rows": torch.stack([_arrange_rows(c.weight.detach().float().to(dev)) for c, _ in convs]).contiguous(),
+                "bn_gamma": torch.stack([f(b.weight) for b in bns]), "bn_beta": torch.stack([f(b.bias) for b in bns]),
+                "conv_bias": torch.stack([f(c.bias) for c, _ in convs]),
+                "running_mean": torch.stack([f(b.running_mean) for b in bns]),
+                "running_var": torch.stack([f(b.running_var) for b in bns]),
+                "batch_stats": torch.zeros((len(bns), 64), dtype=torch.float32, device=dev),
+            })
         # Device tensors live at STABLE addresses: a refresh copies into the existing storage, so raw pointers baked
         # into a captured CUDA graph (RolloutCollector.collect(graph=True)) keep reading current weights.  A change of
         # shape (another board size / block count) re-allocates and shows up in pointer_signature().
@@ -116,10 +139,37 @@ class NativeResNet:
         self.policy_tail = nn.Sequential(*list(ph)[2:]).to(dev).eval()        # LN, ReLU, Linear, LN, ReLU, Linear
         self.value_tail = nn.Sequential(*list(vh)[2:]).to(dev).eval()          # ... + Tanh
         self.version = getattr(self, "version", 0) + 1
+        if self.bn_mode == "train":
+            self._bn = MnkBnTrain(P["bn_gamma"].data_ptr(), P["bn_beta"].data_ptr(), P["conv_bias"].data_ptr(),
+                                  P["running_mean"].data_ptr(), P["running_var"].data_ptr(), P["batch_stats"].data_ptr(),
+                                  self._bn_momentum, self._bn_eps)
+            self.train_forwards = 0
+
+    @torch.no_grad()
+    def export_running_stats(self, model: nn.Module):
+        """Write the running statistics the train-mode forwards accumulated on the device back into `model`'s
+        BatchNorm buffers (and advance num_batches_tracked by the number of forwards)."""
+        if self.bn_mode != "train":
+            return
+        bns = [model.conv_in[1]] + [b for blk in model.res_blocks for b in (blk.bn1, blk.bn2)]
+        for i, b in enumerate(bns):
+            b.running_mean.copy_(self._params["running_mean"][i])
+            b.running_var.copy_(self._params["running_var"][i])
+            if b.num_batches_tracked is not None:
+                b.num_batches_tracked += self.train_forwards
+        self.train_forwards = 0
+
+    def _train_scratch(self, m: int, n: int, num_envs: int) -> torch.Tensor:
+        need = int(self._L.mnk_resnet_tower_train_scratch_bytes(m, n, num_envs, self.blocks))
+        check(need if need < 0 else 0, "mnk_resnet_tower_train_scratch_bytes")
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=self._dev)
+        return self._scratch
 
     def pointer_signature(self):
         """Addresses of every device tensor a captured launch reads (see RolloutCollector._collect_graphed)."""
-        return tuple(t.data_ptr() for t in self._params.values()) + (self._err.data_ptr(),)
+        scratch = (self._scratch.data_ptr(),) if self._scratch is not None else ()
+        return tuple(t.data_ptr() for t in self._params.values()) + (self._err.data_ptr(),) + scratch
 
     @torch.no_grad()
     def tails(self, pf: torch.Tensor, vf: torch.Tensor, want_value: bool = True):
@@ -139,6 +189,16 @@ class NativeResNet:
     def features(self, state: MnkState, num_envs: int, cells: int, swap: Optional[torch.Tensor]):
         pf = torch.empty((num_envs, 2 * cells), dtype=torch.float32, device=self._dev)
         vf = torch.empty((num_envs, cells), dtype=torch.float32, device=self._dev)
+        if self.bn_mode == "train":
+            scratch = self._train_scratch(state.m, state.n, num_envs)
+            with torch.cuda.device(self._dev):
+                check(self._L.mnk_resnet_tower_train(
+                    ctypes.byref(state), None if swap is None else swap.data_ptr(), self._params["raw_rows"].data_ptr(),
+                    ctypes.byref(self._bn), self.head_w.data_ptr(), self.head_b.data_ptr(), self.blocks, scratch.data_ptr(),
+                    scratch.numel(), pf.data_ptr(), vf.data_ptr(), self._err.data_ptr(),
+                    torch.cuda.current_stream(self._dev).cuda_stream), "mnk_resnet_tower_train")
+            self.train_forwards += 1
+            return pf, vf
         rows = self.use_rows_kernel and ROWS_KERNEL_BOARD_ROWS[0] <= state.m <= ROWS_KERNEL_BOARD_ROWS[1]
         entry, name, weights = ((self._L.mnk_resnet_tower_rows, "mnk_resnet_tower_rows", self.weights_rows) if rows else
                                 (self._L.mnk_resnet_tower, "mnk_resnet_tower", self.weights))

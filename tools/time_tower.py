@@ -11,7 +11,7 @@ m, n, k = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (9, 9, 5)))
 flops_per_sample = {(9, 9): 12.136e6, (13, 13): 25.3e6, (19, 19): 54.1e6}[(m, n)]
 torch.manual_seed(0)
 net = ResNetActorCritic((2, m, n), m * n).cuda().eval()
-native = NativeResNet(net)
+native = NativeResNet(net, bn_mode=os.environ.get("MNK_BN", "eval"))
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops_sustained": 1391.8}
 for ne in (4096, 32768, 262144)[: int(os.environ.get('MNK_SIZES', 3))]:
     env = TorchVectorMnkEnv(m, n, k, ne, device="cuda")
@@ -57,4 +57,16 @@ for ne in (4096, 32768, 262144)[: int(os.environ.get('MNK_SIZES', 3))]:
     tf = ne * flops_per_sample * 0.98 / (ms * 1e-3) / 1e12
     print(f"{m}x{n} envs={ne}: tower {ms:.3f} ms = {ne/ms*1e3/1e6:.2f} M samples/s = {tf:.1f} useful TFLOP/s "
           f"({tf/peaks['bf16_tflops_sustained']:.3f} of sustained bf16 peak); heads kernel {ms_heads:.3f} ms; forward_env {ms_full:.3f} ms (with torch heads {ms_torch:.3f} ms)")
+    if os.environ.get("MNK_BN") == "train" and ne <= 32768:      # the same forward in stock PyTorch (cuDNN, train-mode BatchNorm)
+        obs = env.observe()["observation"]
+        net.train()
+        with torch.no_grad():
+            for _ in range(2):
+                net(obs, None)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(5):
+                net(obs, None)
+            e1.record(); torch.cuda.synchronize()
+        print(f"    stock PyTorch train-mode forward (TF32 convs allowed): {e0.elapsed_time(e1) / 5:.3f} ms")
 native.check_error()
