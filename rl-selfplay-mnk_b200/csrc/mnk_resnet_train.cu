@@ -54,7 +54,6 @@ constexpr int kMmaWarp = kEpiWarps;
 constexpr int kWatchWarp = kMmaWarp + 1;
 constexpr int kThreads = 32 * (kWatchWarp + 1);
 constexpr u32 kIdesc = umma_idesc_bf16(kN);
-constexpr int kRowBatch = 5;                  // transform: skip rows fetched per batch (registers)
 
 struct Smem {
     alignas(128) unsigned char wts[kLayerWeightBytes];
@@ -73,6 +72,7 @@ struct Params {
     int m, n, words, layer;
     long long num_envs, groups;
     int epc, pw;
+    int reverse;                      // walk the groups from the last to the first
     const u64* bits;
     const uint8_t* swap;
     const unsigned char* z_in;        // fp16 [groups][4][m][128][8]
@@ -103,20 +103,38 @@ MNK_DEV uint4 ldg128(const void* ptr) {
     asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
     return v;
 }
-MNK_DEV void l2_prefetch(const void* ptr, u32 bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-}
 MNK_DEV float2 half2_to_float2(u32 w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
 MNK_DEV u32 float2_to_half2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const u32*>(&h);
 }
 
+MNK_DEV void tmem_ld8_issue(u32 taddr, u32 (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+MNK_DEV void tmem_ld8_wait(u32 (&a)[8], u32 (&b)[8], u32 (&c)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
+                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]),
+                   "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7])
+                 :
+                 : "memory");
+}
+
+// Pipeline (per CTA, global block / step index g = group * m + board row, groups back to back with no drain):
+//   MMA block g      waits for epilogue step g - lead (its TMEM slot is free AND its operand row is in shared memory)
+//   epilogue step e  first produces the operand row of block e + lead (transform of the raw fp16 row the TMA delivered, or
+//                    the bitboard decode), then waits for the commit of block e + 1, moves its three TMEM slices to
+//                    registers, accumulates the statistics, stores z and releases step e
+//   raw z of group j is fetched by TMA into buffer j & 1 at MMA block (j-1, lead-1): every MMA of group j-2 is complete there
+//                    (that block waited for step (j-2, m-1)), and the first transform of group j is lead steps away
 __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m = p.m, cells = p.m * p.n;
+    const int m = p.m;
     const int plane16 = m * 128 + 2 * kPad;                  // rows (16-byte units) per k-chunk plane
     const int buf16 = kChunks * plane16;                     // 16-byte units per operand buffer
     uint4* const act = reinterpret_cast<uint4*>(&sm.act[0]);
@@ -126,6 +144,12 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
     const size_t group_bytes = kChunks * plane_bytes;
     const int total_steps = my_groups * m;
     const int lead = min(kLead, m);
+    // this CTA's i-th group; consecutive launches walk the groups in opposite directions, so a launch starts on what
+    // the previous one wrote last (still in L2)
+    auto group_of = [&](int i) -> long long {
+        const long long g = (long long)blockIdx.x + (long long)i * gridDim.x;
+        return p.reverse ? p.groups - 1 - g : g;
+    };
 
     // ---- one-time setup -----------------------------------------------------------------------------
     if (tid == 0) {
@@ -136,11 +160,13 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(&sm.wts_bar, kLayerWeightBytes);
         tma_bulk_g2s(&sm.wts[0], p.weights, kLayerWeightBytes, &sm.wts_bar);
-        if (!first) {   // z of this CTA's first group
-            const unsigned char* src = p.z_in + (size_t)blockIdx.x * group_bytes;
-            mbar_expect_tx(&sm.in_bar[0], (u32)group_bytes);
-            for (int c = 0; c < kChunks; ++c)
-                tma_bulk_g2s(act + c * plane16 + kPad, src + c * plane_bytes, (u32)plane_bytes, &sm.in_bar[0]);
+        if (!first) {   // raw z of this CTA's first two groups
+            for (int i = 0; i < min(2, my_groups); ++i) {
+                const unsigned char* src = p.z_in + (size_t)group_of(i) * group_bytes;
+                mbar_expect_tx(&sm.in_bar[i], (u32)group_bytes);
+                for (int c = 0; c < kChunks; ++c)
+                    tma_bulk_g2s(act + i * buf16 + c * plane16 + kPad, src + c * plane_bytes, (u32)plane_bytes, &sm.in_bar[i]);
+            }
         }
     }
     if (warp == kMmaWarp) {
@@ -167,33 +193,31 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
     bool ok = true;
 
     if (warp == kMmaWarp) {
-        // ================= MMA issue (one elected lane) + prefetch of the next group's operand ====================
+        // ================= MMA issue (one elected lane) + TMA of the raw operand two groups ahead ===================
         ok = __all_sync(MNK_FULL_WARP, mbar_wait(&sm.wts_bar, 0)) != 0;
+        if (!ok && p.error != nullptr) atomicMax(p.error, 0x100 | p.layer);
         const u64 b_d0 = umma_desc(smem_u32(&sm.wts[0]), kN * 16, 128);
         const u32 b_lo0 = (u32)b_d0, b_hi = (u32)(b_d0 >> 32);
         const u32 act_lo = smem_u32(&sm.act[0]) + kPad * 16;
+        asm volatile("bar.sync %0, %1;" ::"r"(kReadyBarrier), "r"(kEpiThreads + 32) : "memory");   // rows 0 .. lead-1 of group 0
         int g = 0;
         for (int i = 0; i < my_groups; ++i) {
             const int buf = i & 1;
-            // operand of group i transformed; every epilogue warp has also left group i-1, so the other buffer is free
-            asm volatile("bar.sync %0, %1;" ::"r"(kReadyBarrier), "r"(kEpiThreads + 32) : "memory");
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (!first && i + 1 < my_groups && elect_one()) {
-                const size_t goff = ((size_t)blockIdx.x + (size_t)(i + 1) * gridDim.x) * group_bytes;
-                uint4* dst = act + (buf ^ 1) * buf16 + kPad;
-                mbar_expect_tx(&sm.in_bar[buf ^ 1], (u32)group_bytes);
-                for (int c = 0; c < kChunks; ++c)
-                    tma_bulk_g2s(dst + c * plane16, p.z_in + goff + c * plane_bytes, (u32)plane_bytes, &sm.in_bar[buf ^ 1]);
-                if (p.skip_in != nullptr)
-                    for (int c = 0; c < kChunks; ++c) l2_prefetch(p.skip_in + goff + c * plane_bytes, (u32)plane_bytes);
-            }
-            __syncwarp();
             const u64 a_d0 = umma_desc(act_lo + (u32)(buf * buf16) * 16, (u32)plane16 * 16, 128);
             const u32 a_lo0 = (u32)a_d0, a_hi = (u32)(a_d0 >> 32);
             for (int b = 0; b < m; ++b, ++g) {
-                if (g >= lead)   // TMEM slot free: steps g-6 .. g-4 read Q_{g-5}
+                if (g >= lead)
                     asm volatile("bar.sync %0, %1;" ::"r"(kStepBarrier0 + (g - lead) % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (!first && b == lead - 1 && i >= 1 && i + 1 < my_groups && elect_one()) {
+                    // step (i-1, m-1) is released: every MMA that read buffer (i+1) & 1 (group i-1) has completed
+                    const size_t goff = (size_t)group_of(i + 1) * group_bytes;
+                    uint4* dst = act + (buf ^ 1) * buf16 + kPad;
+                    mbar_expect_tx(&sm.in_bar[buf ^ 1], (u32)group_bytes);
+                    for (int c = 0; c < kChunks; ++c)
+                        tma_bulk_g2s(dst + c * plane16, p.z_in + goff + c * plane_bytes, (u32)plane_bytes, &sm.in_bar[buf ^ 1]);
+                }
+                __syncwarp();
                 const int slot = g % kSlots;
                 const u32 d_tmem = tmem_base + (u32)(slot * kN);
                 const u32 a_row = a_lo0 + (u32)(b * 128 - 1);            // kx = 0 reads lane p-1
@@ -217,138 +241,182 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
         for (int e = 0; e < total_steps; ++e) {
             const int r = e % m;
             const int need = (r < m - 1) ? e + 1 : e;
+            const bool was = ok;
             ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[need % kSlots], (u32)(need / kSlots) & 1u)) != 0;
+            if (was && !ok && p.error != nullptr && lane == 0) atomicMax(p.error, 0x200 | p.layer);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.arrive %0, %1;" ::"r"(kTokenBarrier0 + e % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");
         }
     } else {
-        // ================= transform (all 16 warps) + epilogue (two sets on alternate steps) =======================
-        const int t_chunk = tid >> 7, t_pos = tid & 127;                 // transform: k-chunk and lane of this thread
-        const int t_s = t_pos / p.pw, t_c = t_pos - t_s * p.pw;
+        // ================= operand rows + epilogue (two sets of 8 warps on alternate steps) ========================
         const int quarter = warp & 3, half = (warp >> 2) & 1, set = warp / kSetWarps;
         const int pos = quarter * 32 + lane;                             // epilogue: TMEM lane
         const int e_s = pos / p.pw, e_c = pos - e_s * p.pw;
         const u32 t_lane = tmem_base + ((u32)(quarter * 32) << 16) + (u32)(16 * half);
+        // operand rows: a set's 256 threads cover one row (128 lanes x 4 k-chunks): lane t_pos, k-chunks t_c0 and t_c0 + 2
+        const int tis = tid & (32 * kSetWarps - 1);
+        const int t_c0 = tis >> 7, t_pos = tis & 127;
+        const int t_s = t_pos / p.pw, t_c = t_pos - t_s * p.pw;
+        const bool t_lane_ok = t_s < p.epc && t_c < p.n;
+        int waited = -1;
+
+        // raw material of the operand row (jt, bt), fetched one own step ahead: the skip operand (two 16-byte units), or
+        // for the input layer the two bitboard words + the swap flag of this lane's cell
+        auto fetch = [&](int jt, int bt, uint4& f0, uint4& f1) {
+            const long long G = group_of(jt);
+            if (first) {
+                const long long en = G * p.epc + t_s;
+                f0 = make_uint4(0, 0, 0, 0);
+                f1 = make_uint4(0, 0, 0, 0);
+                if (t_c0 == 0 && t_lane_ok && en < p.num_envs) {
+                    const int bit = bt * p.pw + t_c;
+                    const u64 wb = p.bits[(size_t)(bit >> 6) * p.num_envs + en];
+                    const u64 ww = p.bits[(size_t)(p.words + (bit >> 6)) * p.num_envs + en];
+                    const u32 black = (u32)(wb >> (bit & 63)) & 1u, white = (u32)(ww >> (bit & 63)) & 1u;
+                    const bool sw = p.swap != nullptr && p.swap[en] != 0;
+                    f0.x = (sw ? white : black) * kActOne | ((sw ? black : white) * kActOne) << 16;
+                }
+            } else if (p.skip_in != nullptr) {
+                const unsigned char* src = p.skip_in + (size_t)G * group_bytes + (size_t)t_c0 * plane_bytes + (size_t)(bt * 128 + t_pos) * 16;
+                f0 = ldg128(src);
+                f1 = ldg128(src + 2 * plane_bytes);
+            }
+        };
+        auto produce = [&](int jt, int bt, const uint4& f0, const uint4& f1) {
+            const int buf = jt & 1;
+            if (first) {
+                if (t_c0 == 0 && t_lane_ok) act[buf * buf16 + kPad + bt * 128 + t_pos] = f0;
+                return;
+            }
+            if (jt != waited) {
+                // the vote also re-converges the warp after the spin loop: the named barriers and tcgen05.ld below are
+                // .aligned (all 32 lanes must execute them together)
+                const bool landed = __all_sync(MNK_FULL_WARP, mbar_wait(&sm.in_bar[buf], (u32)(jt >> 1) & 1u)) != 0;
+                if (!landed && ok && p.error != nullptr) atomicMax(p.error, 0x400 | p.layer);
+                ok = ok && landed;
+                waited = jt;
+            }
+            const long long G = group_of(jt);
+            const int envs_here = (int)min((long long)p.epc, p.num_envs - G * p.epc);
+            const bool valid = t_s < envs_here && t_c < p.n;
+            const u32 keep = valid ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int chunk = t_c0 + 2 * u;
+                uint4* unit = act + buf * buf16 + chunk * plane16 + kPad + bt * 128 + t_pos;
+                const uint4 zq = *unit;
+                const uint4 sk = u == 0 ? f0 : f1;
+                const float4 sc0 = *reinterpret_cast<const float4*>(&sm.scale[chunk * 8]);
+                const float4 sc1 = *reinterpret_cast<const float4*>(&sm.scale[chunk * 8 + 4]);
+                const float4 sh0 = *reinterpret_cast<const float4*>(&sm.shift[chunk * 8]);
+                const float4 sh1 = *reinterpret_cast<const float4*>(&sm.shift[chunk * 8 + 4]);
+                const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+                const u32 zw[4] = {zq.x, zq.y, zq.z, zq.w};
+                const u32 kw[4] = {sk.x, sk.y, sk.z, sk.w};
+                u32 ow[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const float2 z2 = half2_to_float2(zw[h]);
+                    float y0 = fmaf(z2.x, sc[2 * h], sh[2 * h]);
+                    float y1 = fmaf(z2.y, sc[2 * h + 1], sh[2 * h + 1]);
+                    if (p.skip_in != nullptr) {
+                        const float2 k2 = act_unpack2(kw[h]);
+                        y0 += k2.x;
+                        y1 += k2.y;
+                    }
+                    ow[h] = act_pack2(fmaxf(y0, 0.0f), fmaxf(y1, 0.0f)) & keep;     // guard / unused lanes -> 0
+                }
+                const uint4 out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                *unit = out;
+                if (p.a_out != nullptr)
+                    stg128(p.a_out + (size_t)G * group_bytes + (size_t)chunk * plane_bytes + (size_t)(bt * 128 + t_pos) * 16, out);
+            }
+        };
+
+        // ---- prologue: operand rows 0 .. lead-1 of this CTA's first group (both sets, two rows each pass) ------------
+        for (int bt = set; bt < lead; bt += kEpiSets) {
+            uint4 f0 = make_uint4(0, 0, 0, 0), f1 = f0;
+            fetch(0, bt, f0, f1);
+            produce(0, bt, f0, f1);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.arrive %0, %1;" ::"r"(kReadyBarrier), "r"(kEpiThreads + 32) : "memory");
+
         float s1[16], s2[16];
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch) s1[ch] = s2[ch] = 0.0f;
-        int e = set;
+        int e = set, j = 0, r = set;                         // this set's step: group j, board row r (m >= 3 > set)
+        int jt = (set + lead) / m, bt = (set + lead) - jt * m;     // the operand row this step produces: block e + lead
         int col = (set % kSlots) * kN;
         int bar = set % kSlots;
-        for (int i = 0; i < my_groups; ++i) {
-            const long long G = (long long)blockIdx.x + (long long)i * gridDim.x;
-            const long long env0 = G * p.epc;
-            const int envs_here = (int)min((long long)p.epc, p.num_envs - env0);
-            const int buf = i & 1;
-            // ---- operand of group i ----------------------------------------------------------------------
-            if (first) {
-                uint4* plane = act + buf * buf16 + kPad;
-                for (int idx = tid; idx < p.epc * cells; idx += kEpiThreads) {
-                    const int s = idx / cells, cell = idx - s * cells;
-                    const int r = cell / p.n, c = cell - r * p.n, bit = cell + r;
-                    u32 word = 0;
-                    if (s < envs_here) {
-                        const long long en = env0 + s;
-                        const u64 wb = p.bits[(size_t)(bit >> 6) * p.num_envs + en];
-                        const u64 ww = p.bits[(size_t)(p.words + (bit >> 6)) * p.num_envs + en];
-                        const bool sw = p.swap != nullptr && p.swap[en] != 0;
-                        const u32 black = (u32)(wb >> (bit & 63)) & 1u, white = (u32)(ww >> (bit & 63)) & 1u;
-                        const u32 me = sw ? white : black, enemy = sw ? black : white;
-                        word = me * kActOne | (enemy * kActOne) << 16;
-                    }
-                    plane[r * 128 + s * p.pw + c] = make_uint4(word, 0, 0, 0);
-                }
-            } else {
-                ok = mbar_wait(&sm.in_bar[buf], (u32)(i >> 1) & 1u) && ok;
-                const bool valid = t_s < envs_here && t_c < p.n;
-                float sc[8], sh[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    sc[j] = valid ? sm.scale[t_chunk * 8 + j] : 0.0f;      // guard / unused lanes: ReLU(0 * z + 0) = 0 ...
-                    sh[j] = valid ? sm.shift[t_chunk * 8 + j] : 0.0f;
-                }
-                const u32 keep = valid ? 0xFFFFFFFFu : 0u;                 // ... and the skip operand is masked too
-                uint4* plane = act + buf * buf16 + t_chunk * plane16 + kPad + t_pos;
-                const size_t goff = (size_t)G * group_bytes + (size_t)t_chunk * plane_bytes + (size_t)t_pos * 16;
-                for (int r0 = 0; r0 < m; r0 += kRowBatch) {
-                    uint4 sk[kRowBatch];
-                    if (p.skip_in != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < kRowBatch; ++j)
-                            if (r0 + j < m) sk[j] = ldg128(p.skip_in + goff + (size_t)(r0 + j) * 2048);
-                    }
-#pragma unroll
-                    for (int j = 0; j < kRowBatch; ++j) {
-                        if (r0 + j < m) {
-                            const uint4 zq = plane[(r0 + j) * 128];
-                            const u32 zw[4] = {zq.x, zq.y, zq.z, zq.w};
-                            u32 ow[4];
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                const float2 z2 = half2_to_float2(zw[h]);
-                                float y0 = fmaf(z2.x, sc[2 * h], sh[2 * h]);
-                                float y1 = fmaf(z2.y, sc[2 * h + 1], sh[2 * h + 1]);
-                                if (p.skip_in != nullptr) {
-                                    const u32 sw4[4] = {sk[j].x, sk[j].y, sk[j].z, sk[j].w};
-                                    const float2 k2 = act_unpack2(sw4[h] & keep);
-                                    y0 += k2.x;
-                                    y1 += k2.y;
-                                }
-                                ow[h] = act_pack2(fmaxf(y0, 0.0f), fmaxf(y1, 0.0f));
-                            }
-                            const uint4 out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                            plane[(r0 + j) * 128] = out;
-                            if (p.a_out != nullptr) stg128(p.a_out + goff + (size_t)(r0 + j) * 2048, out);
-                        }
-                    }
-                }
+        uint4 f0 = make_uint4(0, 0, 0, 0), f1 = f0;
+        if (jt < my_groups) fetch(jt, bt, f0, f1);
+        while (e < total_steps) {
+            if (jt < my_groups) {
+                produce(jt, bt, f0, f1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.arrive %0, %1;" ::"r"(kReadyBarrier), "r"(kEpiThreads + 32) : "memory");
-            // ---- this set's epilogue steps of group i --------------------------------------------------
-            const bool e_valid = e_s < envs_here && e_c < p.n;
-            unsigned char* zrow = p.z_out + (size_t)G * group_bytes + (size_t)(2 * half) * plane_bytes + (size_t)pos * 16;
-            const int e_end = (i + 1) * m;
-            while (e < e_end) {
-                const int r = e - i * m;
-                asm volatile("bar.sync %0, %1;" ::"r"(kTokenBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const bool up = r > 0, down = r < m - 1;
-                const int col_up = up ? (col == 0 ? (kSlots - 1) * kN : col - kN) : col;
-                const int col_down = down ? (col == (kSlots - 1) * kN ? 0 : col + kN) : col;
-                u32 q0[16], q1[16], q2[16];
-                tmem_ld16_issue(t_lane + (u32)col_up, q0);
-                tmem_ld16_issue(t_lane + (u32)(col + kC), q1);
-                tmem_ld16_issue(t_lane + (u32)(col_down + 2 * kC), q2);
-                tmem_ld_wait(q0);
-                tmem_ld_wait(q1);
-                tmem_ld_wait(q2);
-                float v[16];
+            asm volatile("bar.sync %0, %1;" ::"r"(kTokenBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool up = r > 0, down = r < m - 1;
+            const int col_up = up ? (col == 0 ? (kSlots - 1) * kN : col - kN) : col;
+            const int col_down = down ? (col == (kSlots - 1) * kN ? 0 : col + kN) : col;
+            float v[16];
 #pragma unroll
-                for (int ch = 0; ch < 16; ++ch) {
+            for (int hh = 0; hh < 2; ++hh) {     // 8 channels at a time: 24 registers in flight instead of 48
+                u32 q0[8], q1[8], q2[8];
+                tmem_ld8_issue(t_lane + (u32)(col_up + 8 * hh), q0);
+                tmem_ld8_issue(t_lane + (u32)(col + kC + 8 * hh), q1);
+                tmem_ld8_issue(t_lane + (u32)(col_down + 2 * kC + 8 * hh), q2);
+                tmem_ld8_wait(q0, q1, q2);
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) {
                     float a = __uint_as_float(q1[ch]);
                     if (up) a += __uint_as_float(q0[ch]);
                     if (down) a += __uint_as_float(q2[ch]);
-                    v[ch] = e_valid ? a : 0.0f;
+                    v[8 * hh + ch] = a;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            const bool arrive_now = jt < my_groups;
+            // raw material for this set's next step
+            bt += kEpiSets;
+            if (bt >= m) { bt -= m; ++jt; }
+            if (jt < my_groups) fetch(jt, bt, f0, f1);
+            // statistics + fp16 store of row (j, r), from registers
+            {
+                const long long G = group_of(j);
+                const int envs_here = (int)min((long long)p.epc, p.num_envs - G * p.epc);
+                const bool e_valid = e_s < envs_here && e_c < p.n;
+#pragma unroll
+                for (int ch = 0; ch < 16; ++ch) {
+                    v[ch] = e_valid ? v[ch] : 0.0f;
                     s1[ch] += v[ch];
                     s2[ch] = fmaf(v[ch], v[ch], s2[ch]);
                 }
+                unsigned char* zrow = p.z_out + (size_t)G * group_bytes + (size_t)(2 * half) * plane_bytes + (size_t)(r * 128 + pos) * 16;
 #pragma unroll
                 for (int kc = 0; kc < 2; ++kc) {
                     u32 w[4];
 #pragma unroll
                     for (int h = 0; h < 4; ++h) w[h] = float2_to_half2(v[kc * 8 + 2 * h], v[kc * 8 + 2 * h + 1]);
-                    stg128(zrow + (size_t)kc * plane_bytes + (size_t)r * 2048, make_uint4(w[0], w[1], w[2], w[3]));
+                    stg128(zrow + (size_t)kc * plane_bytes, make_uint4(w[0], w[1], w[2], w[3]));
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                if (e + lead < total_steps)
-                    asm volatile("bar.arrive %0, %1;" ::"r"(kStepBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
-                e += kEpiSets;
-                col += kEpiSets * kN;
-                if (col >= kSlots * kN) col -= kSlots * kN;
-                bar += kEpiSets;
-                if (bar >= kSlots) bar -= kSlots;
             }
+            // Step e is released only here, at its very end, as in the eval-mode kernel.  Releasing it right after the TMEM
+            // loads (slot free, operand row written) looked safe on paper and deadlocked one CTA in ~1,000 launches on
+            // B200 (watcher timeout near the end of the CTA's last group; 31 of 60 forwards at 32,768 envs, none with this
+            // placement -- tools/debug_train.py).
+            if (arrive_now)
+                asm volatile("bar.arrive %0, %1;" ::"r"(kStepBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
+            e += kEpiSets;
+            r += kEpiSets;
+            if (r >= m) { r -= m; ++j; }
+            col += kEpiSets * kN;
+            if (col >= kSlots * kN) col -= kSlots * kN;
+            bar += kEpiSets;
+            if (bar >= kSlots) bar -= kSlots;
         }
         // per-warp sums of this warp's 16 channels over its 32 lanes
 #pragma unroll
@@ -370,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (!ok && p.error != nullptr) atomicExch(p.error, 1);
+    if (!ok && p.error != nullptr) atomicMax(p.error, 1);
     if (warp == kMmaWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
@@ -416,6 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
 // a_last = ReLU(BN(z_last) [+ skip]) and the 1x1 convolutions that open the two heads; one thread per (group, row, lane)
 struct FeatParams {
     int m, n, epc, pw;
+    int reverse;             // start with the groups the last layer launch wrote last
     long long num_envs, groups;
     const unsigned char* z_in;
     const unsigned char* skip_in;
@@ -435,8 +504,8 @@ __global__ void __launch_bounds__(256) resnet_train_features_kernel(FeatParams p
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per_group = (long long)p.m * 128;
     if (idx >= p.groups * per_group) return;
-    const long long G = idx / per_group;
-    const int rp = (int)(idx - G * per_group), r = rp >> 7, pos = rp & 127;
+    const long long G = p.reverse ? p.groups - 1 - idx / per_group : idx / per_group;
+    const int rp = (int)(idx % per_group), r = rp >> 7, pos = rp & 127;
     const int s = pos / p.pw, c = pos - s * p.pw;
     const long long env = G * p.epc + s;
     if (s >= p.epc || c >= p.n || env >= p.num_envs) return;
@@ -528,6 +597,7 @@ extern "C" int mnk_resnet_tower_train(const mnk_state_t* st, const uint8_t* swap
         p.m = st->m; p.n = st->n; p.words = st->words; p.layer = L;
         p.num_envs = st->num_envs; p.groups = lay.groups;
         p.pw = st->n + 1; p.epc = 128 / p.pw;
+        p.reverse = L & 1;
         p.bits = reinterpret_cast<const u64*>(st->bits); p.swap = swap;
         const int in = L - 1;                                  // the operand of this launch is a_in
         p.z_in = L > 0 ? base + lay.z[in & 1] : nullptr;
@@ -552,6 +622,7 @@ extern "C" int mnk_resnet_tower_train(const mnk_state_t* st, const uint8_t* swap
     const int last = layers - 1;
     f.m = st->m; f.n = st->n; f.pw = st->n + 1; f.epc = 128 / f.pw;
     f.num_envs = st->num_envs; f.groups = lay.groups;
+    f.reverse = (last & 1) ? 0 : 1;
     f.z_in = base + lay.z[last & 1];
     f.skip_in = (last >= 2 && (last & 1) == 0) ? base + lay.a[((last - 2) / 2) & 1] : nullptr;
     f.scale_shift = scale_shift + (size_t)last * 64;

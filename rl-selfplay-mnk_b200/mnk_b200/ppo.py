@@ -4,7 +4,8 @@
 one call = one rollout of ``n_steps`` agent steps over all envs (``RolloutCollector``: observation
 carried across calls, on-device episode statistics), GAE (``mnk_gae``), then ``ppo_epochs`` passes of
 clipped-surrogate minibatch updates (:168-262) whose minibatches are re-materialised from the packed
-buffer (``mnk_rollout_gather``).  The update itself is stock PyTorch autograd (bf16 autocast, gradient
+buffer (``mnk_rollout_gather``).  The rollout's forward runs on the tcgen05 path with train-mode BatchNorm
+(``NativeResNet(bn_mode="train")``, as the reference's rollout does); the update itself is stock PyTorch autograd (bf16 autocast, gradient
 clipping at 0.5, the caller's optimiser) -- the learner is outside the hot path.
 
 Data parallel: with ``world_size > 1`` every rank collects from its own env shard and the ranks stay in
@@ -45,7 +46,8 @@ class PPOAgent:
                  clip_range=0.2, ppo_epochs=4, batch_size=64, value_coef=0.5, entropy_coef=0.01, num_envs=1,
                  device="cuda", lr_scheduler=None, entropy_scheduler=None, k: Optional[int] = None,
                  autocast_dtype: Optional[torch.dtype] = torch.bfloat16, seed: int = 0, env_offset: int = 0,
-                 world_size: int = 1, process_group=None, max_grad_norm: float = 0.5):
+                 world_size: int = 1, process_group=None, max_grad_norm: float = 0.5, native_rollout: bool = True,
+                 graph_rollout: bool = False):
         self.device = torch.device(device)
         self.network = network.to(self.device)
         self.optimizer = optimizer
@@ -62,17 +64,35 @@ class PPOAgent:
                                           process_group=process_group, world_size=world_size)
         if world_size > 1:          # replicas start from rank 0's parameters / buffers / optimiser state
             broadcast_module(self.network, self.optimizer, group=process_group)
+        # Rollout forward on the tcgen05 path with TRAIN-mode BatchNorm -- the reference's rollout never leaves train
+        # mode (src/alg/ppo.py:97) -- for the accelerated architecture (resnet_b_s layout, boards up to 10 rows); any
+        # other module keeps the generic path (stock PyTorch forward on f32 observations).
+        self.native, self.graph_rollout = None, graph_rollout
+        if native_rollout and obs_shape[1] <= 10:
+            from .resnet import NativeResNet
+            try:
+                self.native = NativeResNet(self.network, device=self.device, bn_mode="train")
+            except (ValueError, AttributeError):
+                self.native = None
 
     # ------------------------------------------------------------------ reference :78-166
     def learn(self, vec_env) -> TrainingMetrics:
-        stats = self.collector.collect(self.network, vec_env, self.buffer)           # :93-124
-        obs = self.collector._last_obs
-        with torch.no_grad():                                                        # :131-135 bootstrap value
-            _, last_values = self.network(obs["observation"], obs["action_mask"])
+        native = self.native is not None and hasattr(vec_env, "_side")
+        if native:
+            stats = self.collector.collect(self.native, vec_env, self.buffer, graph=self.graph_rollout)       # :93-124
+            _, last_values = self.native.forward_env(vec_env.env, swap=vec_env._side)    # :131-135 (train mode there too)
+            self.native.export_running_stats(self.network)      # the update continues from the rollout's statistics
+        else:
+            stats = self.collector.collect(self.network, vec_env, self.buffer)
+            obs = self.collector._last_obs
+            with torch.no_grad():                                                    # :131-135 bootstrap value
+                _, last_values = self.network(obs["observation"], obs["action_mask"])
         self.buffer.compute_advantages_and_returns(last_values.reshape(self.num_envs), self.gamma, self.gae_lambda)
         learn_start = time.time()
         metrics = self.update_networks()
         learn_time = time.time() - learn_start
+        if native:
+            self.native.refresh(self.network)                   # new weights (and the update's running statistics)
         if self.lr_scheduler:
             self.lr_scheduler.step()
         if self.entropy_scheduler:

@@ -159,6 +159,19 @@ class NativeResNet:
                 b.num_batches_tracked += self.train_forwards
         self.train_forwards = 0
 
+    def running_state(self):
+        """Copies of the device-side running statistics (+ the forward count): restore_running_state() undoes forwards
+        that must not count, e.g. the allocation warm-up before a CUDA-graph capture."""
+        if self.bn_mode != "train":
+            return None
+        return self._params["running_mean"].clone(), self._params["running_var"].clone(), self.train_forwards
+
+    def restore_running_state(self, state):
+        if state is not None:
+            self._params["running_mean"].copy_(state[0])
+            self._params["running_var"].copy_(state[1])
+            self.train_forwards = state[2]
+
     def _train_scratch(self, m: int, n: int, num_envs: int) -> torch.Tensor:
         need = int(self._L.mnk_resnet_tower_train_scratch_bytes(m, n, num_envs, self.blocks))
         check(need if need < 0 else 0, "mnk_resnet_tower_train_scratch_bytes")

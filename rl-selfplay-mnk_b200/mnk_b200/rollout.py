@@ -230,7 +230,10 @@ class RolloutCollector:
         old = getattr(self, "_graph_key", None)
         if old is None or len(old) != len(key) or any(a is not b and a != b for a, b in zip(old, key)):
             with torch.no_grad():                          # one-time work that must not happen under capture
-                network.forward_env(vec_env.env, swap=vec_env._side)
+                state = network.running_state() if hasattr(network, "running_state") else None
+                network.forward_env(vec_env.env, swap=vec_env._side)       # (scratch allocation, shared-memory opt-in)
+                if state is not None:                      # a train-mode BatchNorm forward: it must not count
+                    network.restore_running_state(state)
                 opp = vec_env.opponent_policy
                 if hasattr(opp, "net"):
                     opp.net.forward_env(vec_env.env)
@@ -247,6 +250,8 @@ class RolloutCollector:
             self._graph_replays = 0
         else:
             self._graph_base += 1 << 24                    # fresh counter range for this replay
+            if hasattr(network, "train_forwards"):         # (the capture pass counted the first replay's forwards)
+                network.train_forwards += steps
         buffer.ptr = 0
         self._graph_totals.zero_()
         self._graph.replay()

@@ -36,3 +36,101 @@ def test_ppo_learns_tictactoe_against_random():
     print(f"score vs random: {s0:.3f} -> {s1:.3f}; mean_reward {history[0].mean_reward:.3f} -> {history[-1].mean_reward:.3f}")
     assert s1 > s0 + 0.08 and s1 > 0.62
     assert history[-1].mean_reward > history[0].mean_reward
+
+
+def _synthetic_rollout(m, n, k, ne, steps, seed):
+    """Transitions with the statistics of a real rollout: mid-game canonical observations of the CUDA env, legal
+    actions, random values / log-probs, sparse terminal rewards."""
+    from mnk_b200 import TorchVectorMnkEnv
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    env = TorchVectorMnkEnv(m, n, k, ne, device=DEV)
+    env.reset()
+    rows = []
+    for t in range(steps):
+        obs = env.observe()
+        a = env.random_legal_actions(seed, t)
+        done = (torch.rand(ne, generator=g) < 0.1).to(DEV)
+        reward = torch.where(done, torch.randint(-1, 2, (ne,), generator=g).float().to(DEV), torch.zeros(ne, device=DEV))
+        rows.append((obs["observation"].clone(), a.clone(), reward, (torch.randn(ne, generator=g) * 0.3).to(DEV).view(-1, 1),
+                     (-torch.rand(ne, generator=g) * 3).to(DEV), done, obs["action_mask"].clone()))
+        env.step_autoreset(a, materialise=False)
+    last = (torch.randn(ne, generator=g) * 0.3).to(DEV)
+    return rows, last
+
+
+@pytest.mark.parametrize("autocast,epochs,batch", [(None, 1, 768), (None, 2, 192), (torch.bfloat16, 2, 192)],
+                         ids=["fp32-one-update", "fp32-8-updates", "bf16-autocast-8-updates"])
+def test_update_networks_matches_the_reference_update(autocast, epochs, batch):
+    """PPOAgent.update_networks() against the UNMODIFIED reference's update (src/alg/ppo.py:168-262, oracle/_ref) on the
+    same network weights, the same rollout and the same minibatch order (torch.randperm patched to a recorded sequence):
+    the seven reported metrics and every parameter / BatchNorm buffer afterwards.  The reference trains on its f32
+    [T, N, 2, m, n] buffer, the drop-in on the packed buffer + mnk_rollout_gather.  One update (whole rollout = one
+    minibatch, SGD) must agree to fp32 rounding; over 8 clipped updates the two runs drift apart like any two fp32 runs
+    of a BatchNorm network (cuDNN's atomics-ordered weight gradients), so those cases get a percent-level bound."""
+    from unittest import mock
+    from oracle import ref_tree
+    if not ref_tree.available():
+        pytest.skip("reference tree neither mounted nor staged (oracle/_ref)")
+    from mnk_b200 import PPOAgent, ResNetActorCritic
+    ppo, hw, cfg, rb = ref_tree.load("alg.ppo", "utils.hardware", "alg.architectures.configs", "alg.rollout_buffer")
+    m, n, k, ne, steps = 9, 9, 5, 96, 8
+    torch.manual_seed(3)
+    ref_net = cfg.ResNetSActorCritic((2, m, n), m * n).to(DEV)
+    net = ResNetActorCritic((2, m, n), m * n).to(DEV)
+    net.load_state_dict(ref_net.state_dict())
+    ref_net.train(), net.train()
+    init = {key: v.clone() for key, v in ref_net.state_dict().items()}
+    # fp32: plain SGD, so parameter differences are proportional to gradient differences; bf16: the reference's AdamW
+    make_opt = (lambda mod: torch.optim.SGD(mod.parameters(), lr=0.05)) if autocast is None else \
+        (lambda mod: torch.optim.AdamW(mod.parameters(), lr=1e-3))
+    kw = dict(n_steps=steps, gamma=0.99, gae_lambda=0.95, clip_range=0.2, ppo_epochs=epochs, batch_size=batch, value_coef=0.5,
+              entropy_coef=0.01, num_envs=ne)
+    ref_agent = ppo.PPOAgent((2, m, n), m * n, ref_net, hw_config=hw.HardwareConfig("cuda", autocast or torch.float32, False, None),
+                             optimizer=make_opt(ref_net), **kw)
+    agent = PPOAgent((2, m, n), m * n, net, optimizer=make_opt(net), device=DEV, k=k,
+                     autocast_dtype=autocast, native_rollout=False, **kw)
+    # a second, identical copy of the reference: how far two runs of the SAME code drift apart (cuDNN's atomics-ordered
+    # weight gradients, amplified by every further update) calibrates the multi-update bound
+    ref_net2 = cfg.ResNetSActorCritic((2, m, n), m * n).to(DEV)
+    ref_net2.load_state_dict(ref_net.state_dict())
+    ref_net2.train()
+    ref_agent2 = ppo.PPOAgent((2, m, n), m * n, ref_net2, hw_config=hw.HardwareConfig("cuda", autocast or torch.float32, False, None),
+                              optimizer=make_opt(ref_net2), **kw)
+    rows, last = _synthetic_rollout(m, n, k, ne, steps, seed=5)
+    for row in rows:
+        ref_agent.buffer.add(*row)
+        ref_agent2.buffer.add(*row)
+        agent.buffer.add(*row)
+    ref_agent.buffer.compute_advantages_and_returns(last, 0.99, 0.95)
+    ref_agent2.buffer.compute_advantages_and_returns(last, 0.99, 0.95)
+    agent.buffer.compute_advantages_and_returns(last, 0.99, 0.95)
+    assert torch.equal(ref_agent.buffer.advantages, agent.buffer.advantages)
+    assert torch.equal(ref_agent.buffer.returns, agent.buffer.returns)
+    assert torch.equal(ref_agent.buffer.observations, agent.buffer.observations)
+    perms = [torch.randperm(steps * ne, generator=torch.Generator().manual_seed(100 + i)).to(DEV) for i in range(epochs)]
+    with mock.patch("torch.randperm", side_effect=[p.clone() for p in perms]):
+        want = ref_agent.update_networks()
+    with mock.patch("torch.randperm", side_effect=[p.clone() for p in perms]):
+        ref_agent2.update_networks()
+    with mock.patch("torch.randperm", side_effect=[p.clone() for p in perms]):
+        got = agent.update_networks()
+    one = epochs == 1 and batch == steps * ne
+    names = ("actor_loss", "critic_loss", "entropy_loss", "grad_norm", "clip_fraction", "explained_variance", "approx_kl")
+    tol = 2e-5 if one else 5e-2
+    for name, a, b in zip(names, want, got):
+        print(f"  {name}: reference {a:+.6f}  drop-in {b:+.6f}")
+        assert abs(a - b) <= tol * max(1.0, abs(a)), name
+    # parameters and BatchNorm buffers: distance between the two results relative to the size of the update itself
+    num = num2 = den = 0.0
+    ref_sd, ref_sd2, sd = ref_net.state_dict(), ref_net2.state_dict(), net.state_dict()
+    for key in ref_sd:
+        if "num_batches" in key:
+            assert int(ref_sd[key]) == int(sd[key])
+            continue
+        num += float((ref_sd[key] - sd[key]).double().pow(2).sum())
+        num2 += float((ref_sd[key] - ref_sd2[key]).double().pow(2).sum())
+        den += float((ref_sd[key] - init[key]).double().pow(2).sum())
+    drift, self_drift = (num / den) ** 0.5, (num2 / den) ** 0.5
+    print(f"  |drop-in - reference| / |reference - initial| over all parameters and buffers = {drift:.2e} "
+          f"(two runs of the reference itself: {self_drift:.2e})")
+    assert drift <= (1e-4 if one else max(0.02, 10 * self_drift))
