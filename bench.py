@@ -663,7 +663,7 @@ def bench_env_workload(ctx: Ctx, wl: Workload, args, primary: bool):
 # ------------------------------------------------------------------------------------------------
 # B200 arm: cfg3, self-play rollout with the policy/value network
 # ------------------------------------------------------------------------------------------------
-def bench_rollout(ctx: Ctx, args, envs: int, agent_bn: str):
+def bench_rollout(ctx: Ctx, args, envs: int, agent_bn: str, extras: bool = True):
     """BASELINE cfg3 per GPU: 9x9x5, agent and opponent both resnet_b_s (same random-init weights, opponent frozen),
     tcgen05 forward fed from bitboards, Gumbel-max sampling, fused wrapper, packed PPO buffer, on-device episode
     statistics; K rollout steps timed.  Metric = the reference's fps (ppo.py:126-129): agent steps / s.
@@ -680,9 +680,8 @@ def bench_rollout(ctx: Ctx, args, envs: int, agent_bn: str):
     torch.manual_seed(0)
     net = ResNetActorCritic((2, m, n), cells).to(dev)
     net.train(agent_bn == "train")
-    agent = NativeResNet(net, device=dev, bn_mode=agent_bn) if "bn_mode" in NativeResNet.__init__.__code__.co_varnames \
-        else NativeResNet(net, device=dev)
-    agent_mode = getattr(agent, "bn_mode", "eval")
+    agent = NativeResNet(net, device=dev, bn_mode=agent_bn)
+    agent_mode = agent.bn_mode
     opponent = NativeNNPolicy(copy.deepcopy(net), device=dev, seed=7)
     env = TorchVectorMnkEnv(m, n, k, envs, device=f"cuda:{ctx.local_rank}", env_offset=rank * envs)
     wr = TorchSelfPlayWrapper(env, seed=SEED)
@@ -715,13 +714,17 @@ def bench_rollout(ctx: Ctx, args, envs: int, agent_bn: str):
     walls = ctx.reduce(walls, "max")
     ms, wall_ms = statistics.median(per), statistics.median(walls)
     if rank != 0:
+        del buf, warm_buf, col, wr, env, agent, opponent
+        torch.cuda.empty_cache()
+        if extras and agent_mode == "train":          # every rank takes part in the eval-mode variant's barriers
+            bench_rollout(ctx, args, envs, "eval", extras=False)
         return None
     peak, peak_src = measured_peak("bf16_tflops_sustained")
     flop_per_agent_step = 2 * FLOP_PER_FORWARD[(m, n)]      # agent + opponent forward
     total = envs * world * K
     value = total / (ms * 1e-3)
     achieved = value * flop_per_agent_step / 1e12 / world   # per GPU, against the per-GPU peak
-    launches = getattr(col, "launches_per_step", 10)
+    launches = 19 if agent_mode == "train" else 10       # kernels per agent step (the train-mode tower is 9 layer launches + 1)
     line = {
         "metric": "self-play rollout steps/sec (9x9x5, resnet_b_s agent + opponent)", "value": value, "unit": "agent-steps/s",
         "n_gpus": world, "steps": K, "warmup": warm_buf.n_steps, "ms_per_step": ms / K, "higher_is_better": True,
@@ -736,7 +739,11 @@ def bench_rollout(ctx: Ctx, args, envs: int, agent_bn: str):
                    "parallelism": f"env-shard x{world}, one NCCL all-reduce of 6 doubles per rollout"},
         "timing": {"replays": reps, "ms_median": ms, "ms_min": min(per), "ms_max": max(per)},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "resnet tower kernels (agent + opponent forward per agent-step)",
+                     "traffic": None,
+                     "kernel": ("resnet_layer_train_kernel x 9 + resnet_train_features_kernel (agent, batch-statistics BatchNorm: fp16 "
+                                "pre-activations round-trip through HBM between the layer launches, ~156 KB per env and forward) + "
+                                "resnet_tower_rows_kernel (opponent)" if agent_mode == "train" else
+                                "resnet_tower_rows_kernel (agent + opponent forward per agent-step)"),
                      "flop_per_agent_step": flop_per_agent_step, "peak_source": peak_src, "per_gpu": True},
         "e2e": {"value": total / (wall_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 64.0 / K,
                 "api": "RolloutCollector.collect (wall clock incl. the statistics all-reduce and host read)"},
@@ -745,13 +752,24 @@ def bench_rollout(ctx: Ctx, args, envs: int, agent_bn: str):
         "stats": {"episodes": stats.episodes, "mean_reward": stats.mean_reward, "mean_length": stats.mean_length,
                   "wins": stats.wins, "losses": stats.losses, "draws": stats.draws},
     }
+    del buf, warm_buf, col, wr, env, agent, opponent
+    torch.cuda.empty_cache()
+    if not extras:
+        return line
+    if agent_mode == "train":
+        # the same rollout with the agent's BatchNorm frozen (eval mode: ONE fused tower kernel instead of one launch per
+        # layer) -- NOT what the reference's rollout computes (ppo.py:97 stays in train mode); reported for the record
+        ev = bench_rollout(ctx, args, envs, "eval", extras=False)
+        if ev is not None:
+            line["eval_mode_agent_variant"] = {
+                "value": ev["value"], "unit": ev["unit"], "ms_per_step": ev["ms_per_step"], "roofline_frac": ev["roofline"]["frac"],
+                "note": "agent BatchNorm in eval mode (frozen statistics, whole tower fused into one kernel); the reference's "
+                        "rollout forward uses batch statistics, so the headline of this line is the train-mode figure"}
     if world == 1 and not args.no_cpu_baseline:
         wl = Workload("cfg2", 1)
         base = cpu_rollout_run(wl, args.cpu_rollout_envs, args.cpu_rollout_steps, 20.0)
         if base is not None:
             line["cpu_baseline"] = base
-    del buf, warm_buf
-    torch.cuda.empty_cache()
     return line
 
 

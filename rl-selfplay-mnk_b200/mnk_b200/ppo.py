@@ -109,7 +109,11 @@ class PPOAgent:
         updates = 0
         buf = self.buffer
         # global advantage statistics (== the single-process normalisation of rollout_buffer.py:96-99)
-        adv_mean, adv_std = global_mean_std(buf.advantages[:buf.ptr], group=self.group)
+        if self.world_size > 1:
+            adv_mean, adv_std = global_mean_std(buf.advantages[:buf.ptr], group=self.group)
+        else:       # the reference's own arithmetic (fp32 mean / unbiased std of the flattened rollout)
+            flat = buf.advantages[:buf.ptr].view(-1)
+            adv_mean, adv_std = flat.mean(), flat.std()
         # every rank must join the same number of gradient all-reduces: with uneven shards the ranks agree on the
         # smallest minibatch count (all-reduce MIN) and the longer loaders drop their last batches
         n_batches = common_minibatches(-(-buf.ptr * buf.num_envs // self.batch_size), self.world_size, self.group, dev)

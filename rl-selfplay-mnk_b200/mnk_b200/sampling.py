@@ -99,10 +99,11 @@ class MaskedCategorical:
 
     def entropy(self) -> torch.Tensor:
         if self._needs_autograd() or not self._raw.is_cuda:
+            # torch.distributions.Categorical.entropy, operation for operation (so that the learner's gradients equal the
+            # reference's bit for bit): clamp keeps -inf out of the product and of its gradient, probs = softmax(logits)
             lg = self.logits
-            finite = torch.isfinite(lg)
-            lg0 = torch.where(finite, lg, torch.zeros_like(lg))      # keeps -inf out of the product AND of its gradient
-            return -(lg0.exp() * finite * lg0).sum(dim=1)
+            p_log_p = torch.clamp(lg, min=torch.finfo(lg.dtype).min) * torch.softmax(lg, dim=-1)
+            return -p_log_p.sum(-1)
         given = torch.zeros(self._raw.shape[0], dtype=torch.long, device=self._raw.device)
         return masked_sample(self._raw, self._mask, given=given, want_log_prob=False, want_entropy=True)[2]
 

@@ -65,8 +65,11 @@ def test_update_networks_matches_the_reference_update(autocast, epochs, batch):
     same network weights, the same rollout and the same minibatch order (torch.randperm patched to a recorded sequence):
     the seven reported metrics and every parameter / BatchNorm buffer afterwards.  The reference trains on its f32
     [T, N, 2, m, n] buffer, the drop-in on the packed buffer + mnk_rollout_gather.  One update (whole rollout = one
-    minibatch, SGD) must agree to fp32 rounding; over 8 clipped updates the two runs drift apart like any two fp32 runs
-    of a BatchNorm network (cuDNN's atomics-ordered weight gradients), so those cases get a percent-level bound."""
+    minibatch, SGD) must agree to fp32 rounding (measured: 1.6e-8 of the update's size; the entropy and the advantage
+    normalisation follow the reference operation for operation).  Eight clipped updates amplify any last-bit difference
+    -- the unmodified reference's own 8-update critic loss moved from 0.442911 to 0.442713 between two processes on the
+    same B200 -- so those cases get a percent-level bound; the second reference copy in this process shows the
+    in-process repeatability next to the number."""
     from unittest import mock
     from oracle import ref_tree
     if not ref_tree.available():
@@ -116,7 +119,7 @@ def test_update_networks_matches_the_reference_update(autocast, epochs, batch):
         got = agent.update_networks()
     one = epochs == 1 and batch == steps * ne
     names = ("actor_loss", "critic_loss", "entropy_loss", "grad_norm", "clip_fraction", "explained_variance", "approx_kl")
-    tol = 2e-5 if one else 5e-2
+    tol = 2e-6 if one else 5e-3 if autocast is None else 3e-2
     for name, a, b in zip(names, want, got):
         print(f"  {name}: reference {a:+.6f}  drop-in {b:+.6f}")
         assert abs(a - b) <= tol * max(1.0, abs(a)), name
@@ -133,4 +136,4 @@ def test_update_networks_matches_the_reference_update(autocast, epochs, batch):
     drift, self_drift = (num / den) ** 0.5, (num2 / den) ** 0.5
     print(f"  |drop-in - reference| / |reference - initial| over all parameters and buffers = {drift:.2e} "
           f"(two runs of the reference itself: {self_drift:.2e})")
-    assert drift <= (1e-4 if one else max(0.02, 10 * self_drift))
+    assert drift <= (1e-5 if one else 2e-2 if autocast is None else 0.1)

@@ -17,7 +17,7 @@ env.reset()
 for t in range(20):
     env.step_autoreset(env.random_legal_actions(1, t), materialise=False)
 bad = 0
-for rep in range(int(os.environ.get("REPS", 4))):
+for rep in range(int(os.environ.get("REPS", 3))):
     native._err.zero_()
     torch.cuda.synchronize()
     t0 = time.time()
