@@ -316,6 +316,17 @@ typedef struct mnk_heads_weights {
 int mnk_resnet_heads(const float* policy_feat, const float* value_feat, int64_t rows, int32_t cells,
                      const mnk_heads_weights_t* w, float* logits, float* values, void* stream);
 
+/* The same head tails with the three multi-output Linear layers as tcgen05 GEMMs over tiles of 128 samples
+ * (csrc/mnk_heads_mma.cu; boards up to 96 cells, MNK_ERR_GEOM otherwise): op16 operands, fp32 accumulation,
+ * LayerNorm / bias / ReLU / Tanh in fp32.  Weight layouts (op16, 16-byte aligned, zero padded; Kp = K rounded up to 16):
+ *   w1p [Kp(2A)/8][128][8]: element (k, n) = policy Linear(2A,128).weight[n][k]      w1v [Kp(A)/8][128][8]: value Linear(A,128)
+ *   w2  [16][Np][8], Np = A rounded up to 16: element (k, n) = policy Linear(128,A).weight[n][k]
+ *   params f32: p_ln1_w[2A] p_ln1_b[2A] v_ln1_w[A] v_ln1_b[A] p_b1 v_b1 p_ln2_w p_ln2_b v_ln2_w v_ln2_b v_w2 (128 each) p_b2[A] v_b2[1]
+ * `values` NULL skips the value head; `error` (may be NULL) is raised to 2 if an internal barrier wait timed out. */
+int mnk_resnet_heads_mma(const float* policy_feat, const float* value_feat, int64_t rows, int32_t cells, const void* w1p,
+                         const void* w1v, const void* w2, const float* params, float* logits, float* values,
+                         int32_t* error, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,7 +116,7 @@ MNK_DEV float2 act_unpack2(u32 w) {
 
 // kind::f16 instruction descriptor: D = f32, A = B = the operand type (fp16: format 0, bf16: format 1), both K-major,
 // M = 128, N = n
-constexpr u32 umma_idesc_bf16(int n) {
+__host__ __device__ constexpr u32 umma_idesc_bf16(int n) {
     return (1u << 4) | (kActF16 ? 0u : ((1u << 7) | (1u << 10))) | ((u32)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 

@@ -136,6 +136,7 @@ SIGNATURES = {
     "mnk_resnet_tower_rows": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "mnk_resnet_tower_train_scratch_bytes": (_I64, [_I32, _I32, _I64, _I32]),
     "mnk_resnet_tower_train": (_I32, [_ST, _VP, _VP, ctypes.POINTER(MnkBnTrain), _VP, _VP, _I32, _VP, _I64, _VP, _VP, _VP, _VP]),
+    "mnk_resnet_heads_mma": (_I32, [_VP, _VP, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mnk_resnet_heads": (_I32, [_VP, _VP, _I64, _I32, ctypes.POINTER(MnkHeadsWeights), _VP, _VP, _VP]),
 }
 

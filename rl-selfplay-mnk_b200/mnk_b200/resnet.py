@@ -54,6 +54,15 @@ def _arrange_rows(w: torch.Tensor) -> torch.Tensor:
     return t.permute(0, 1, 3, 4, 2).reshape(3, 4, 3 * c_out, 8).contiguous().to(operand_dtype())
 
 
+def _arrange_linear(w: torch.Tensor, kpad: int, npad: int) -> torch.Tensor:
+    """Linear.weight [n_out][k_in] fp32 -> UMMA B operand, K-major: operand type [kpad/8][npad][8] (zero padded)."""
+    n, k = w.shape
+    full = torch.zeros((npad, kpad), dtype=torch.float32, device=w.device)
+    full[:n, :k] = w
+    return full.view(npad, kpad // 8, 8).permute(1, 0, 2).contiguous().to(operand_dtype())
+
+
+MMA_HEADS_MAX_CELLS = 96               # mnk_resnet_heads_mma (shared-memory bound); larger boards use the fp32 heads kernel
 ROWS_KERNEL_BOARD_ROWS = (3, 10)      # mnk_resnet_tower_rows: boards with 3 <= m <= 10 rows (shared-memory bound)
 
 
@@ -70,6 +79,7 @@ class NativeResNet:
         self.train_forwards = 0             # train-mode forwards since the last export_running_stats
         self._scratch = None
         self.torch_heads = torch_heads      # run the head tails through the original torch modules (debug / comparison)
+        self.use_mma_heads = True           # tcgen05 head GEMMs where the board fits (<= 96 cells); False = fp32 heads kernel
         self.use_rows_kernel = True         # board-row tower kernel where the board fits it (m <= 10); False = tap kernel
         dev = torch.device(device)
         if dev.type != "cuda":
@@ -108,6 +118,17 @@ class NativeResNet:
             "v_ln1_w": f(vh[2].weight), "v_ln1_b": f(vh[2].bias), "v_w1t": f(vh[4].weight.t()), "v_b1": f(vh[4].bias),
             "v_ln2_w": f(vh[5].weight), "v_ln2_b": f(vh[5].bias), "v_w2": f(vh[7].weight.reshape(-1)), "v_b2": f(vh[7].bias),
         }
+        cells_h = ph[7].out_features
+        if cells_h <= MMA_HEADS_MAX_CELLS:   # tcgen05 heads: the three Linear weights as UMMA B operands + one parameter vector
+            r16 = lambda v: (v + 15) // 16 * 16
+            fresh.update({
+                "hm_w1p": _arrange_linear(f(ph[4].weight), r16(2 * cells_h), 128),
+                "hm_w1v": _arrange_linear(f(vh[4].weight), r16(cells_h), 128),
+                "hm_w2": _arrange_linear(f(ph[7].weight), 128, r16(cells_h)),
+                "hm_params": torch.cat([f(t).reshape(-1) for t in (
+                    ph[2].weight, ph[2].bias, vh[2].weight, vh[2].bias, ph[4].bias, vh[4].bias, ph[5].weight, ph[5].bias,
+                    vh[5].weight, vh[5].bias, vh[7].weight, ph[7].bias, vh[7].bias)]).contiguous(),
+            })
         if self.bn_mode == "train":          # unfolded conv weights + BatchNorm parameters / running statistics, [L][32]
             bns = [b for _, b in convs]
             if any(b.momentum != bns[0].momentum or b.eps != bns[0].eps or not b.track_running_stats for b in bns):
@@ -192,6 +213,15 @@ class NativeResNet:
         rows, cells = vf.shape
         logits = torch.empty((rows, cells), dtype=torch.float32, device=self._dev)
         values = torch.empty((rows, 1), dtype=torch.float32, device=self._dev) if want_value else None
+        if self.use_mma_heads and "hm_w2" in self._params:
+            P = self._params
+            with torch.cuda.device(self._dev):
+                check(self._L.mnk_resnet_heads_mma(pf.data_ptr(), vf.data_ptr(), rows, cells, P["hm_w1p"].data_ptr(),
+                                                    P["hm_w1v"].data_ptr(), P["hm_w2"].data_ptr(), P["hm_params"].data_ptr(),
+                                                    logits.data_ptr(), values.data_ptr() if want_value else None,
+                                                    self._err.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream),
+                      "mnk_resnet_heads_mma")
+            return logits, values
         with torch.cuda.device(self._dev):
             check(self._L.mnk_resnet_heads(pf.data_ptr(), vf.data_ptr(), rows, cells, ctypes.byref(self._heads),
                                             logits.data_ptr(), values.data_ptr() if want_value else None,

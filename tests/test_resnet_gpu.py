@@ -226,6 +226,7 @@ def test_fused_heads_match_torch_modules(m, n):
                 mod.bias.normal_(0, 0.2)
         net.policy_head[7].weight.mul_(40.0)
     native = NativeResNet(net, device=DEV)
+    native.use_mma_heads = False
     for rows in (1, 8, 13, 1001):
         pf = torch.randn(rows, 2 * cells, device=DEV) * 2
         vf = torch.randn(rows, cells, device=DEV) * 2
@@ -237,6 +238,49 @@ def test_fused_heads_match_torch_modules(m, n):
         assert torch.allclose(values, want_v, rtol=1e-4, atol=1e-5), (values - want_v).abs().max()
         only_l, none_v = native.tails(pf, vf, want_value=False)        # policy-only (values = NULL in the C ABI)
         assert none_v is None and torch.equal(only_l, logits)
+
+
+@pytest.mark.parametrize("m,n", [(9, 9), (3, 3), (5, 7), (8, 12), (6, 6)], ids=lambda v: str(v))
+def test_tensor_core_heads_match_torch_modules(m, n):
+    """mnk_resnet_heads_mma (the three Linear layers as tcgen05 GEMMs over 128-sample tiles, 16-bit operands, fp32
+    accumulation / LayerNorm / bias) against the torch modules in fp32 and against the fp32 heads kernel: row counts
+    with a partial tile and several tiles per CTA, policy-only calls; element-wise error bound 1e-3 of the logit range
+    (the budget the tower + heads share in test_native_forward_matches_reference)."""
+    from mnk_b200 import NativeResNet, ResNetActorCritic
+    torch.manual_seed(7)
+    cells = m * n
+    net = ResNetActorCritic((2, m, n), cells).to(DEV).eval()
+    with torch.no_grad():
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.LayerNorm):
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.normal_(0, 0.3)
+            elif isinstance(mod, torch.nn.Linear):
+                mod.bias.normal_(0, 0.2)
+        net.policy_head[7].weight.mul_(40.0)
+    native = NativeResNet(net, device=DEV)
+    assert native.use_mma_heads and "hm_w2" in native._params
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        for rows in (1, 127, 128, 129, 1001, 148 * 128 * 2 + 77):
+            pf = torch.randn(rows, 2 * cells, device=DEV) * 2
+            vf = torch.randn(rows, cells, device=DEV) * 2
+            logits, values = native.tails(pf, vf)
+            native.check_error()
+            with torch.no_grad():
+                want_l, want_v = native.policy_tail(pf), native.value_tail(vf)
+            assert logits.shape == want_l.shape and values.shape == want_v.shape
+            scale = float(want_l.abs().max())
+            err, rel = float((logits - want_l).abs().max()), float((logits - want_l).norm() / want_l.norm())
+            verr = float((values - want_v).abs().max())
+            if rows in (1, 1001):
+                print(f"{m}x{n} rows={rows}: logits max|d| {err:.2e} (scale {scale:.1f}) rel_l2 {rel:.2e}; value max|d| {verr:.2e}")
+            assert err <= 1e-3 * scale and rel <= 4e-4 and verr <= 2e-3, (rows, err, scale, rel, verr)
+            only_l, none_v = native.tails(pf, vf, want_value=False)    # policy-only (values = NULL in the C ABI)
+            assert none_v is None and torch.equal(only_l, logits)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
 
 
 @pytest.mark.parametrize("opponent_kind", ["native_nn", "random"])
