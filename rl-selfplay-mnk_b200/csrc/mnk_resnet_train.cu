@@ -90,6 +90,7 @@ struct Params {
     float* out_scale_shift;           // f32 [64] of layer L
     float* batch_stats;               // null or f32 [64]: batch mean (conv bias included), biased variance
     unsigned int* counter;
+    unsigned int* postmortem;         // u32 [16] in the scratch buffer, zeroed per forward
     float momentum, eps;
     double count;                     // num_envs * m * n
     int* error;
@@ -130,6 +131,9 @@ MNK_DEV void tmem_ld8_wait(u32 (&a)[8], u32 (&b)[8], u32 (&c)[8]) {
 //                    registers, accumulates the statistics, stores z and releases step e
 //   raw z of group j is fetched by TMA into buffer j & 1 at MMA block (j-1, lead-1): every MMA of group j-2 is complete there
 //                    (that block waited for step (j-2, m-1)), and the first transform of group j is lead steps away
+// kFirst: the input layer (operand decoded from the bitboards); kSkip: the operand adds a skip activation; kAOut: the
+// operand is also written to HBM (a block input).  Compile-time, so that the per-step code carries no dead branches.
+template <bool kFirst, bool kSkip, bool kAOut>
 __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
     const int plane16 = m * 128 + 2 * kPad;                  // rows (16-byte units) per k-chunk plane
     const int buf16 = kChunks * plane16;                     // 16-byte units per operand buffer
     uint4* const act = reinterpret_cast<uint4*>(&sm.act[0]);
-    const bool first = p.layer == 0;
+    constexpr bool first = kFirst;
     const int my_groups = (int)((p.groups - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const size_t plane_bytes = (size_t)m * 128 * 16;
     const size_t group_bytes = kChunks * plane_bytes;
@@ -244,11 +248,24 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
             const bool was = ok;
             ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[need % kSlots], (u32)(need / kSlots) & 1u)) != 0;
             if (was && !ok && p.error != nullptr && lane == 0) atomicMax(p.error, 0x200 | p.layer);
+            // post-mortem of the first timeout (never taken in a healthy run): which CTA / step / layer, and the five commit
+            // barriers' raw words, into the scratch buffer (tools/debug_train.py prints them)
+            if (was && !ok && lane == 0 && atomicAdd(p.postmortem, 1u) == 0u) {
+                p.postmortem[1] = blockIdx.x | ((unsigned)total_steps << 16);
+                p.postmortem[2] = (unsigned)e | ((unsigned)p.layer << 16);
+                for (int q = 0; q < kSlots; ++q) {
+                    p.postmortem[4 + 2 * q] = (unsigned)(sm.mma_bar[q] & 0xFFFFFFFFull);
+                    p.postmortem[5 + 2 * q] = (unsigned)(sm.mma_bar[q] >> 32);
+                }
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("bar.arrive %0, %1;" ::"r"(kTokenBarrier0 + e % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");
         }
     } else {
         // ================= operand rows + epilogue (two sets of 8 warps on alternate steps) ========================
+        // Everything that depends only on the group (its index in HBM, how many of its envs exist, this thread's
+        // validity, base pointers) is refreshed when the group changes, not every step: integer / address arithmetic was
+        // half of the ~400 instructions a warp executed per step (ncu opcode histogram, profiles/README.md).
         const int quarter = warp & 3, half = (warp >> 2) & 1, set = warp / kSetWarps;
         const int pos = quarter * 32 + lane;                             // epilogue: TMEM lane
         const int e_s = pos / p.pw, e_c = pos - e_s * p.pw;
@@ -258,16 +275,38 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
         const int t_c0 = tis >> 7, t_pos = tis & 127;
         const int t_s = t_pos / p.pw, t_c = t_pos - t_s * p.pw;
         const bool t_lane_ok = t_s < p.epc && t_c < p.n;
-        int waited = -1;
-
-        // raw material of the operand row (jt, bt), fetched one own step ahead: the skip operand (two 16-byte units), or
-        // for the input layer the two bitboard words + the swap flag of this lane's cell
-        auto fetch = [&](int jt, int bt, uint4& f0, uint4& f1) {
+        uint4* const unit0 = act + t_c0 * plane16 + kPad + t_pos;        // this thread's unit of row 0, buffer 0, first k-chunk
+        const size_t t_off = (size_t)t_c0 * plane_bytes + (size_t)t_pos * 16;    // the same unit inside a group in HBM
+        const size_t e_off = (size_t)(2 * half) * plane_bytes + (size_t)pos * 16;
+        // producer-side group state (group jt of the operand row being produced) and epilogue-side (group j)
+        int pg = -1;
+        u32 p_keep = 0;
+        size_t p_goff = 0;
+        long long p_env = 0;
+        bool p_here = false;
+        auto enter_producer_group = [&](int jt) {
+            pg = jt;
             const long long G = group_of(jt);
-            if (first) {
+            const int envs_here = (int)min((long long)p.epc, p.num_envs - G * p.epc);
+            p_keep = (t_s < envs_here && t_c < p.n) ? 0xFFFFFFFFu : 0u;
+            p_goff = (size_t)G * group_bytes + t_off;
+            p_env = G * p.epc + t_s;
+            p_here = t_c0 == 0 && t_lane_ok && t_s < envs_here;
+            if constexpr (!kFirst) {
+                // buffer jt & 1 holds the raw rows of group jt.  The vote also re-converges the warp after the spin loop:
+                // the named barriers and tcgen05.ld below are .aligned (all 32 lanes must execute them together)
+                const bool landed = __all_sync(MNK_FULL_WARP, mbar_wait(&sm.in_bar[jt & 1], (u32)(jt >> 1) & 1u)) != 0;
+                if (!landed && ok && p.error != nullptr) atomicMax(p.error, 0x400 | p.layer);
+                ok = ok && landed;
+            }
+        };
+        // raw material of the operand row (jt, bt), fetched one own step ahead: the skip operand (two 16-byte units), or
+        // for the input layer the packed stones of this lane's cell
+        auto fetch = [&](int jt, int bt, uint4& f0, uint4& f1) {
+            if constexpr (kFirst) {
+                const long long G = group_of(jt);
                 const long long en = G * p.epc + t_s;
                 f0 = make_uint4(0, 0, 0, 0);
-                f1 = make_uint4(0, 0, 0, 0);
                 if (t_c0 == 0 && t_lane_ok && en < p.num_envs) {
                     const int bit = bt * p.pw + t_c;
                     const u64 wb = p.bits[(size_t)(bit >> 6) * p.num_envs + en];
@@ -276,61 +315,47 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
                     const bool sw = p.swap != nullptr && p.swap[en] != 0;
                     f0.x = (sw ? white : black) * kActOne | ((sw ? black : white) * kActOne) << 16;
                 }
-            } else if (p.skip_in != nullptr) {
-                const unsigned char* src = p.skip_in + (size_t)G * group_bytes + (size_t)t_c0 * plane_bytes + (size_t)(bt * 128 + t_pos) * 16;
+            } else if constexpr (kSkip) {
+                const unsigned char* src = p.skip_in + (size_t)group_of(jt) * group_bytes + t_off + (size_t)bt * 2048;
                 f0 = ldg128(src);
                 f1 = ldg128(src + 2 * plane_bytes);
             }
         };
         auto produce = [&](int jt, int bt, const uint4& f0, const uint4& f1) {
-            const int buf = jt & 1;
-            if (first) {
-                if (t_c0 == 0 && t_lane_ok) act[buf * buf16 + kPad + bt * 128 + t_pos] = f0;
+            if (jt != pg) enter_producer_group(jt);
+            uint4* row = unit0 + (jt & 1) * buf16 + bt * 128;
+            if constexpr (kFirst) {
+                if (t_c0 == 0 && t_lane_ok) *row = f0;
                 return;
-            }
-            if (jt != waited) {
-                // the vote also re-converges the warp after the spin loop: the named barriers and tcgen05.ld below are
-                // .aligned (all 32 lanes must execute them together)
-                const bool landed = __all_sync(MNK_FULL_WARP, mbar_wait(&sm.in_bar[buf], (u32)(jt >> 1) & 1u)) != 0;
-                if (!landed && ok && p.error != nullptr) atomicMax(p.error, 0x400 | p.layer);
-                ok = ok && landed;
-                waited = jt;
-            }
-            const long long G = group_of(jt);
-            const int envs_here = (int)min((long long)p.epc, p.num_envs - G * p.epc);
-            const bool valid = t_s < envs_here && t_c < p.n;
-            const u32 keep = valid ? 0xFFFFFFFFu : 0u;
+            } else {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int chunk = t_c0 + 2 * u;
-                uint4* unit = act + buf * buf16 + chunk * plane16 + kPad + bt * 128 + t_pos;
-                const uint4 zq = *unit;
-                const uint4 sk = u == 0 ? f0 : f1;
-                const float4 sc0 = *reinterpret_cast<const float4*>(&sm.scale[chunk * 8]);
-                const float4 sc1 = *reinterpret_cast<const float4*>(&sm.scale[chunk * 8 + 4]);
-                const float4 sh0 = *reinterpret_cast<const float4*>(&sm.shift[chunk * 8]);
-                const float4 sh1 = *reinterpret_cast<const float4*>(&sm.shift[chunk * 8 + 4]);
-                const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-                const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-                const u32 zw[4] = {zq.x, zq.y, zq.z, zq.w};
-                const u32 kw[4] = {sk.x, sk.y, sk.z, sk.w};
-                u32 ow[4];
+                for (int u = 0; u < 2; ++u) {
+                    uint4* unit = row + u * 2 * plane16;
+                    const uint4 zq = *unit;
+                    const uint4 sk = u == 0 ? f0 : f1;
+                    const float4* ss = reinterpret_cast<const float4*>(&sm.scale[(t_c0 + 2 * u) * 8]);     // shift follows scale
+                    const float4 sc0 = ss[0], sc1 = ss[1], sh0 = ss[8], sh1 = ss[9];
+                    const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                    const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+                    const u32 zw[4] = {zq.x, zq.y, zq.z, zq.w};
+                    const u32 kw[4] = {sk.x, sk.y, sk.z, sk.w};
+                    u32 ow[4];
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const float2 z2 = half2_to_float2(zw[h]);
-                    float y0 = fmaf(z2.x, sc[2 * h], sh[2 * h]);
-                    float y1 = fmaf(z2.y, sc[2 * h + 1], sh[2 * h + 1]);
-                    if (p.skip_in != nullptr) {
-                        const float2 k2 = act_unpack2(kw[h]);
-                        y0 += k2.x;
-                        y1 += k2.y;
+                    for (int h = 0; h < 4; ++h) {
+                        const float2 z2 = half2_to_float2(zw[h]);
+                        float y0 = fmaf(z2.x, sc[2 * h], sh[2 * h]);
+                        float y1 = fmaf(z2.y, sc[2 * h + 1], sh[2 * h + 1]);
+                        if constexpr (kSkip) {
+                            const float2 k2 = act_unpack2(kw[h]);
+                            y0 += k2.x;
+                            y1 += k2.y;
+                        }
+                        ow[h] = act_pack2(fmaxf(y0, 0.0f), fmaxf(y1, 0.0f)) & p_keep;     // guard / unused lanes -> 0
                     }
-                    ow[h] = act_pack2(fmaxf(y0, 0.0f), fmaxf(y1, 0.0f)) & keep;     // guard / unused lanes -> 0
+                    const uint4 out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    *unit = out;
+                    if constexpr (kAOut) stg128(p.a_out + p_goff + (size_t)u * 2 * plane_bytes + (size_t)bt * 2048, out);
                 }
-                const uint4 out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                *unit = out;
-                if (p.a_out != nullptr)
-                    stg128(p.a_out + (size_t)G * group_bytes + (size_t)chunk * plane_bytes + (size_t)(bt * 128 + t_pos) * 16, out);
             }
         };
 
@@ -350,6 +375,9 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
         int jt = (set + lead) / m, bt = (set + lead) - jt * m;     // the operand row this step produces: block e + lead
         int col = (set % kSlots) * kN;
         int bar = set % kSlots;
+        int eg = -1;                                         // epilogue-side group state
+        bool e_valid = false;
+        unsigned char* zgroup = nullptr;
         uint4 f0 = make_uint4(0, 0, 0, 0), f1 = f0;
         if (jt < my_groups) fetch(jt, bt, f0, f1);
         while (e < total_steps) {
@@ -385,17 +413,21 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
             if (bt >= m) { bt -= m; ++jt; }
             if (jt < my_groups) fetch(jt, bt, f0, f1);
             // statistics + fp16 store of row (j, r), from registers
-            {
+            if (j != eg) {
+                eg = j;
                 const long long G = group_of(j);
                 const int envs_here = (int)min((long long)p.epc, p.num_envs - G * p.epc);
-                const bool e_valid = e_s < envs_here && e_c < p.n;
+                e_valid = e_s < envs_here && e_c < p.n;
+                zgroup = p.z_out + (size_t)G * group_bytes + e_off;
+            }
+            {
 #pragma unroll
                 for (int ch = 0; ch < 16; ++ch) {
                     v[ch] = e_valid ? v[ch] : 0.0f;
                     s1[ch] += v[ch];
                     s2[ch] = fmaf(v[ch], v[ch], s2[ch]);
                 }
-                unsigned char* zrow = p.z_out + (size_t)G * group_bytes + (size_t)(2 * half) * plane_bytes + (size_t)(r * 128 + pos) * 16;
+                unsigned char* zrow = zgroup + (size_t)r * 2048;
 #pragma unroll
                 for (int kc = 0; kc < 2; ++kc) {
                     u32 w[4];
@@ -590,8 +622,12 @@ extern "C" int mnk_resnet_tower_train(const mnk_state_t* st, const uint8_t* swap
     cudaError_t e = cudaMemsetAsync(base + lay.counter, 0, 256, s);
     if (e != cudaSuccess) return (int)e;
     const size_t smem = sizeof(rt::Smem) + 128 + (size_t)2 * rt::kChunks * (st->m * 128 + 2 * rt::kPad) * 16;
-    static std::atomic<size_t> granted[kMaxDevices];
-    if (int rc = mnk_optin_smem(rt::resnet_layer_train_kernel, smem, granted)) return rc;
+    static std::atomic<size_t> granted[5][kMaxDevices];
+    if (int rc = mnk_optin_smem(rt::resnet_layer_train_kernel<true, false, false>, smem, granted[0])) return rc;
+    if (int rc = mnk_optin_smem(rt::resnet_layer_train_kernel<false, true, true>, smem, granted[1])) return rc;
+    if (int rc = mnk_optin_smem(rt::resnet_layer_train_kernel<false, true, false>, smem, granted[2])) return rc;
+    if (int rc = mnk_optin_smem(rt::resnet_layer_train_kernel<false, false, true>, smem, granted[3])) return rc;
+    if (int rc = mnk_optin_smem(rt::resnet_layer_train_kernel<false, false, false>, smem, granted[4])) return rc;
     for (int L = 0; L < layers; ++L) {
         rt::Params p;
         p.m = st->m; p.n = st->n; p.words = st->words; p.layer = L;
@@ -612,10 +648,16 @@ extern "C" int mnk_resnet_tower_train(const mnk_state_t* st, const uint8_t* swap
         p.out_scale_shift = scale_shift + (size_t)L * 64;
         p.batch_stats = bn->batch_stats ? bn->batch_stats + L * 64 : nullptr;
         p.counter = reinterpret_cast<unsigned int*>(base + lay.counter);
+        p.postmortem = p.counter + 16;
         p.momentum = bn->momentum; p.eps = bn->eps;
         p.count = (double)st->num_envs * st->m * st->n;
         p.error = error;
-        rt::resnet_layer_train_kernel<<<lay.grid, rt::kThreads, smem, s>>>(p);
+        const bool skip = p.skip_in != nullptr, aout = p.a_out != nullptr;
+        if (L == 0) rt::resnet_layer_train_kernel<true, false, false><<<lay.grid, rt::kThreads, smem, s>>>(p);
+        else if (skip && aout) rt::resnet_layer_train_kernel<false, true, true><<<lay.grid, rt::kThreads, smem, s>>>(p);
+        else if (skip) rt::resnet_layer_train_kernel<false, true, false><<<lay.grid, rt::kThreads, smem, s>>>(p);
+        else if (aout) rt::resnet_layer_train_kernel<false, false, true><<<lay.grid, rt::kThreads, smem, s>>>(p);
+        else rt::resnet_layer_train_kernel<false, false, false><<<lay.grid, rt::kThreads, smem, s>>>(p);
         if (int rc = mnk_launch_status()) return rc;
     }
     rt::FeatParams f;

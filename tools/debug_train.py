@@ -1,4 +1,6 @@
-"""Bounded probe of mnk_resnet_tower_train at a given env count: time per forward and the barrier-timeout flags."""
+"""Soak / post-mortem probe of mnk_resnet_tower_train at a given env count: time per forward and the barrier-timeout flag
+(0x100 weights, 0x200 commit watcher, 0x400 operand TMA; low bits = layer); on a timeout the kernel's post-mortem words
+(CTA, step, layer, raw commit barriers) are read back from the scratch buffer."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "rl-selfplay-mnk_b200")); sys.path.insert(0, ROOT)
@@ -8,27 +10,33 @@ if os.environ.get("MNK_LIB"):
     _lib.LIB_PATH = os.path.abspath(os.environ["MNK_LIB"])
 ne = int(sys.argv[1])
 m, n, k = 9, 9, 5
+reps = int(os.environ.get("REPS", 3))
 torch.manual_seed(0)
 net = ResNetActorCritic((2, m, n), m * n).cuda()
 native = NativeResNet(net, bn_mode="train")
-native._err = torch.zeros(32, dtype=torch.int32, device="cuda")
 env = TorchVectorMnkEnv(m, n, k, ne, device="cuda")
 env.reset()
 for t in range(20):
     env.step_autoreset(env.random_legal_actions(1, t), materialise=False)
 bad = 0
-for rep in range(int(os.environ.get("REPS", 3))):
-    native._err.zero_()
+for rep in range(reps):
     torch.cuda.synchronize()
     t0 = time.time()
     pf, vf = native.features(env._st, ne, m * n, None)
     torch.cuda.synchronize()
     ms = 1e3 * (time.time() - t0)
-    er = native._err.tolist()
-    bad += 1 if er[0] else 0
-    if er[0] or rep < 2 or rep == int(os.environ.get("REPS", 4)) - 1:
-        print(f"envs={ne} forward {rep}: {ms:.2f} ms code {hex(er[0])} layers wts/watch/tma {hex(er[1])}/{hex(er[2])}/{hex(er[3])} "
-              f"watcher e min {100000 - er[4] if er[4] else None} max {er[5]} ctas {er[6]}", flush=True)
-        if er[0]:
-            print(f"    cta {er[7] & 0xFFFF} total_steps {er[7] >> 16}: per-warp (phase, index): " + " ".join(f"{w}:{x >> 16}/{x & 0xFFFF}" for w, x in enumerate(er[8:26])), flush=True)
-print(f"envs={ne}: {bad} of {int(os.environ.get('REPS', 4))} forwards hit a barrier timeout", flush=True)
+    code = int(native._err.item())
+    bad += 1 if code else 0
+    if code or rep < 2 or rep == reps - 1:
+        print(f"envs={ne} forward {rep}: {ms:.2f} ms code {hex(code)}", flush=True)
+    if code:
+        need = int(_lib.lib().mnk_resnet_tower_train_scratch_bytes(m, n, ne, native.blocks))
+        pm = native._scratch[need - 256 + 64: need - 256 + 128].view(torch.int32).tolist()
+        tot = (pm[1] >> 16) & 0xFFFF
+        print(f"    first watcher timeout of this forward: cta {pm[1] & 0xFFFF}, {tot} steps, watcher at step {pm[2] & 0xFFFF} "
+              f"(total-{tot - (pm[2] & 0xFFFF)}), layer {pm[2] >> 16}; commit barriers " +
+              " ".join(hex(((pm[5 + 2 * q] & 0xFFFFFFFF) << 32) | (pm[4 + 2 * q] & 0xFFFFFFFF)) for q in range(5)), flush=True)
+        native._err.zero_()
+    if bad >= int(os.environ.get("MAX_BAD", 3)):
+        break
+print(f"envs={ne}: {bad} of {rep + 1} forwards hit a barrier timeout", flush=True)
