@@ -46,20 +46,25 @@ constexpr int kPad = 8;                       // zero rows before / after each a
 constexpr int kSlots = 5;                     // TMEM ring: 5 x 96 columns
 constexpr int kTmemCols = 512;
 constexpr int kLead = 4;                      // MMA blocks in flight ahead of the epilogue
-constexpr int kTokenBarrier0 = 8;             // named barriers 8..12: "the blocks step e needs are committed" (id 8 + e % 5)
-constexpr int kStepBarrier0 = 3;              // named barriers 3..7: "epilogue step e done" (id 3 + e % 5); 13-15: head exchange of a set
+// Named-barrier ids are per epilogue set: step e uses index e % (2 * sets).  Two ids per set suffice and no id is shared
+// between the sets -- with ids shared across sets (the first version used e % 5 like the TMEM ring) a warp of one set can
+// complete a barrier phase in place of a late warp of the other set at a layer boundary; see mnk_resnet_train.cu.
+constexpr int kTokenBarrier0 = 8;             // named barriers 8..11: "the blocks step e needs are committed" (id 8 + e % 4)
+constexpr int kStepBarrier0 = 3;              // named barriers 3..6: "epilogue step e done" (id 3 + e % 4); 13-14: head exchange of a set
 constexpr int kWtsSlots = 3;
 constexpr int kLayerWeightBytes = 3 * kChunks * kN * 16;   // 18,432
 #ifndef MNK_EPI_SETS
 #define MNK_EPI_SETS 2
 #endif
-constexpr int kEpiSets = MNK_EPI_SETS;                   // two sets of 8 epilogue warps take alternate steps (the step is latency-bound)
+constexpr int kEpiSets = MNK_EPI_SETS;
+constexpr int kBarIds = 2 * kEpiSets;                   // two sets of 8 epilogue warps take alternate steps (the step is latency-bound)
 constexpr int kSetWarps = 8;                  // per set: TMEM lane quarter = warp & 3, channel half = (warp >> 2) & 1
 constexpr int kMmaWarp = kEpiSets * kSetWarps;
 constexpr int kWatchWarp = kMmaWarp + 1;      // turns MMA commits (mbarriers) into named-barrier tokens for the epilogue sets
 constexpr int kThreads = 32 * (kWatchWarp + 1);
 constexpr u32 kIdesc = umma_idesc_bf16(kN);
 static_assert(kEpiSets <= kMinBoardRows && kEpiSets < kSlots, "a set's consecutive steps lie in the same or the next layer");
+static_assert(kEpiSets == 2, "named-barrier ids: 3..6 step, 8..11 token, 13..14 head exchange");
 
 struct Smem {
     alignas(128) unsigned char wts[kWtsSlots][kLayerWeightBytes];
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
                     // Hardware named barrier, not shared memory: while MMAs run, the tensor core's operand reads own the
                     // shared-memory pipe and an LDS / mbarrier poll from this warp waits ~300 cycles behind them (timeline
                     // in profiles/README.md).  The MMA warp consumes one barrier per step, in step order.
-                    asm volatile("bar.sync %0, %1;" ::"r"(kStepBarrier0 + (g - lead) % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");
+                    asm volatile("bar.sync %0, %1;" ::"r"(kStepBarrier0 + (g - lead) % kBarIds), "r"(32 * (kSetWarps + 1)) : "memory");
                 }
                 MNK_STAMP(g, 5);   // epilogue waits passed
                 if (b == 0) {
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
             const int need = (r < m - 1) ? e + 1 : e;            // Q_{r+1} is the last slice row r needs
             ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[need % kSlots], (u32)(need / kSlots) & 1u)) != 0;
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.arrive %0, %1;" ::"r"(kTokenBarrier0 + e % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");
+            asm volatile("bar.arrive %0, %1;" ::"r"(kTokenBarrier0 + e % kBarIds), "r"(32 * (kSetWarps + 1)) : "memory");
         }
     } else {
         // ================= epilogue: one board row (128 lanes x 32 channels) per step, sets alternate steps =========
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
         // instructions this kernel executed: ncu opcode histogram, profiles/README.md).
         int e = set, L = 0, r = set;                 // kEpiSets <= kMinBoardRows: the first step lies in layer 0
         int col = (set % kSlots) * kN;              // TMEM column of slot e % kSlots
-        int bar = set % kSlots;                     // e % kSlots: index of this step's named barriers
+        int bar = set;                              // e % kBarIds: index of this step's named barriers
         bool new_layer = true, skip = false, last = false;
         float bias[16];
         uint4* layer_out = nullptr;
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
             col += kEpiSets * kN;
             if (col >= kSlots * kN) col -= kSlots * kN;
             bar += kEpiSets;
-            if (bar >= kSlots) bar -= kSlots;
+            if (bar >= kBarIds) bar -= kBarIds;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

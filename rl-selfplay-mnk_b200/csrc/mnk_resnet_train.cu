@@ -42,11 +42,22 @@ constexpr int kPad = 8;
 constexpr int kSlots = 5;
 constexpr int kTmemCols = 512;
 constexpr int kLead = 4;
-constexpr int kStepBarrier0 = 3;              // named barriers 3..7: "epilogue step e done" (id 3 + e % 5)
-constexpr int kTokenBarrier0 = 8;             // 8..12: "the blocks step e needs are committed"
+// Named-barrier ids are PER EPILOGUE SET: step e uses index e % (2 * sets) = (its set, the parity of the set's step count).
+// Two ids per set are enough (a set's warps pass token e before any of them reaches token e + 2*sets, and the watcher / the
+// MMA warp cannot send / consume e + 2*sets before e is complete), and no id is shared between the sets.  The first version
+// indexed both families by e % 5 like the TMEM ring, so steps e (one set) and e + 5 (the other set) shared an id -- and at a
+// group boundary (the step of a group's last board row needs no later block, so its token follows the previous one at once)
+// a warp of the faster set could reach the sync of token e + 5 while a warp of the other set had not yet reached the sync of
+// token e: the hardware counts threads, not identities, so the early warp completed e's phase in the slow warp's place, read
+// its TMEM slices before the commit, and the two warps stayed exchanged until one of them ran out of steps at the end of
+// the CTA's last group -- a commit-watcher timeout once in ~10,000 launches (tools/soak_cfg3.py, post-mortem in
+// profiles/README.md).
+constexpr int kEpiSets = 2;
+constexpr int kBarIds = 2 * kEpiSets;
+constexpr int kStepBarrier0 = 3;              // named barriers 3..6: "epilogue step e done" (id 3 + e % 4)
+constexpr int kTokenBarrier0 = 8;             // 8..11: "the blocks step e needs are committed"
 constexpr int kReadyBarrier = 13;             // "the operand of this group is in shared memory"
 constexpr int kLayerWeightBytes = 3 * kChunks * kN * 16;   // 18,432
-constexpr int kEpiSets = 2;
 constexpr int kSetWarps = 8;
 constexpr int kEpiWarps = kEpiSets * kSetWarps;
 constexpr int kEpiThreads = 32 * kEpiWarps;   // 512: also the transform's thread count (4 k-chunks x 128 lanes)
@@ -65,6 +76,9 @@ struct Smem {
     unsigned long long in_bar[2];
     unsigned int tmem_base;
     unsigned int is_last;
+#ifdef MNK_PROGRESS
+    volatile unsigned int prog[24];           // debug build: (index << 4 | stage) of every warp, dumped on a watcher timeout
+#endif
     alignas(128) unsigned char act[1];        // [2 buffers][4 k-chunks][m*128 + 2*kPad rows][16 B]
 };
 
@@ -195,6 +209,11 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const u32 tmem_base = sm.tmem_base;
     bool ok = true;
+#ifdef MNK_PROGRESS
+#define MNK_PROG(idx, stage) do { if (lane == 0) sm.prog[warp] = ((unsigned)(idx) << 4) | (unsigned)(stage); } while (0)
+#else
+#define MNK_PROG(idx, stage) do { } while (0)
+#endif
 
     if (warp == kMmaWarp) {
         // ================= MMA issue (one elected lane) + TMA of the raw operand two groups ahead ===================
@@ -210,8 +229,10 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
             const u64 a_d0 = umma_desc(act_lo + (u32)(buf * buf16) * 16, (u32)plane16 * 16, 128);
             const u32 a_lo0 = (u32)a_d0, a_hi = (u32)(a_d0 >> 32);
             for (int b = 0; b < m; ++b, ++g) {
+                MNK_PROG(g, 1);
                 if (g >= lead)
-                    asm volatile("bar.sync %0, %1;" ::"r"(kStepBarrier0 + (g - lead) % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");
+                    asm volatile("bar.sync %0, %1;" ::"r"(kStepBarrier0 + (g - lead) % kBarIds), "r"(32 * (kSetWarps + 1)) : "memory");
+                MNK_PROG(g, 2);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (!first && b == lead - 1 && i >= 1 && i + 1 < my_groups && elect_one()) {
                     // step (i-1, m-1) is released: every MMA that read buffer (i+1) & 1 (group i-1) has completed
@@ -238,28 +259,46 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
                     umma_commit(&sm.mma_bar[slot]);
                 }
                 __syncwarp();
+                MNK_PROG(g, 3);
             }
         }
+        MNK_PROG(g, 7);
     } else if (warp == kWatchWarp) {
         // ================= commit watcher: MMA commits (mbarriers) -> named-barrier tokens, in step order ==========
         for (int e = 0; e < total_steps; ++e) {
             const int r = e % m;
             const int need = (r < m - 1) ? e + 1 : e;
             const bool was = ok;
+            MNK_PROG(e, 1);
             ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar[need % kSlots], (u32)(need / kSlots) & 1u)) != 0;
             if (was && !ok && p.error != nullptr && lane == 0) atomicMax(p.error, 0x200 | p.layer);
             // post-mortem of the first timeout (never taken in a healthy run): which CTA / step / layer, and the five commit
             // barriers' raw words, into the scratch buffer (tools/debug_train.py prints them)
-            if (was && !ok && lane == 0 && atomicAdd(p.postmortem, 1u) == 0u) {
-                p.postmortem[1] = blockIdx.x | ((unsigned)total_steps << 16);
-                p.postmortem[2] = (unsigned)e | ((unsigned)p.layer << 16);
-                for (int q = 0; q < kSlots; ++q) {
-                    p.postmortem[4 + 2 * q] = (unsigned)(sm.mma_bar[q] & 0xFFFFFFFFull);
-                    p.postmortem[5 + 2 * q] = (unsigned)(sm.mma_bar[q] >> 32);
+            if (was && !ok) {
+                if (lane == 0 && atomicAdd(p.postmortem, 1u) == 0u) {
+                    p.postmortem[1] = blockIdx.x | ((unsigned)total_steps << 16);
+                    p.postmortem[2] = (unsigned)e | ((unsigned)p.layer << 16);
+                    p.postmortem[3] = (unsigned)my_groups;
+                    for (int q = 0; q < kSlots; ++q) {
+                        const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&sm.mma_bar[q]);
+                        p.postmortem[4 + 2 * q] = (unsigned)(w & 0xFFFFFFFFull);
+                        p.postmortem[5 + 2 * q] = (unsigned)(w >> 32);
+                    }
+#ifdef MNK_PROGRESS
+                    for (int q = 0; q < 18; ++q) p.postmortem[14 + q] = sm.prog[q];
+                    for (int q = 0; q < 2; ++q) {
+                        const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&sm.in_bar[q]);
+                        p.postmortem[32 + 2 * q] = (unsigned)(w & 0xFFFFFFFFull);
+                        p.postmortem[33 + 2 * q] = (unsigned)(w >> 32);
+                    }
+#endif
+                    __threadfence();
                 }
+                __syncwarp();      // no token leaves before the dump is complete
             }
+            MNK_PROG(e, 2);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("bar.arrive %0, %1;" ::"r"(kTokenBarrier0 + e % kSlots), "r"(32 * (kSetWarps + 1)) : "memory");
+            asm volatile("bar.arrive %0, %1;" ::"r"(kTokenBarrier0 + e % kBarIds), "r"(32 * (kSetWarps + 1)) : "memory");
         }
     } else {
         // ================= operand rows + epilogue (two sets of 8 warps on alternate steps) ========================
@@ -374,18 +413,21 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
         int e = set, j = 0, r = set;                         // this set's step: group j, board row r (m >= 3 > set)
         int jt = (set + lead) / m, bt = (set + lead) - jt * m;     // the operand row this step produces: block e + lead
         int col = (set % kSlots) * kN;
-        int bar = set % kSlots;
+        int bar = set;                                       // e % kBarIds: index of this step's named barriers
         int eg = -1;                                         // epilogue-side group state
         bool e_valid = false;
         unsigned char* zgroup = nullptr;
         uint4 f0 = make_uint4(0, 0, 0, 0), f1 = f0;
         if (jt < my_groups) fetch(jt, bt, f0, f1);
         while (e < total_steps) {
+            MNK_PROG(e, 1);
             if (jt < my_groups) {
                 produce(jt, bt, f0, f1);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
+            MNK_PROG(e, 2);
             asm volatile("bar.sync %0, %1;" ::"r"(kTokenBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
+            MNK_PROG(e, 3);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const bool up = r > 0, down = r < m - 1;
             const int col_up = up ? (col == 0 ? (kSlots - 1) * kN : col - kN) : col;
@@ -407,7 +449,15 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            MNK_PROG(e, 4);
             const bool arrive_now = jt < my_groups;
+            // Step e is released HERE: its TMEM slices are in registers (slot free) and the operand row of block e + lead was
+            // written before the token sync; the statistics and the stores of row e run under the next MMAs.  (With the
+            // named-barrier ids shared between the sets -- see kBarIds -- this placement deadlocked every second forward and
+            // the release at the very end of the step once in ~10,000 launches; with per-set ids both are clean over 54,000
+            // launches of tools/soak_cfg3.py and this one is 5 % faster.)
+            if (arrive_now)
+                asm volatile("bar.arrive %0, %1;" ::"r"(kStepBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
             // raw material for this set's next step
             bt += kEpiSets;
             if (bt >= m) { bt -= m; ++jt; }
@@ -436,20 +486,17 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
                     stg128(zrow + (size_t)kc * plane_bytes, make_uint4(w[0], w[1], w[2], w[3]));
                 }
             }
-            // Step e is released only here, at its very end, as in the eval-mode kernel.  Releasing it right after the TMEM
-            // loads (slot free, operand row written) looked safe on paper and deadlocked one CTA in ~1,000 launches on
-            // B200 (watcher timeout near the end of the CTA's last group; 31 of 60 forwards at 32,768 envs, none with this
-            // placement -- tools/debug_train.py).
-            if (arrive_now)
-                asm volatile("bar.arrive %0, %1;" ::"r"(kStepBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
+            MNK_PROG(e, 5);
+            MNK_PROG(e, 6);
             e += kEpiSets;
             r += kEpiSets;
             if (r >= m) { r -= m; ++j; }
             col += kEpiSets * kN;
             if (col >= kSlots * kN) col -= kSlots * kN;
             bar += kEpiSets;
-            if (bar >= kSlots) bar -= kSlots;
+            if (bar >= kBarIds) bar -= kBarIds;
         }
+        MNK_PROG(e, 7);
         // per-warp sums of this warp's 16 channels over its 32 lanes
 #pragma unroll
         for (int ch = 0; ch < 16; ++ch) {
@@ -619,7 +666,9 @@ extern "C" int mnk_resnet_tower_train(const mnk_state_t* st, const uint8_t* swap
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     unsigned char* base = static_cast<unsigned char*>(scratch);
     float* scale_shift = reinterpret_cast<float*>(base + lay.scale_shift);
-    cudaError_t e = cudaMemsetAsync(base + lay.counter, 0, 256, s);
+    // the CTA counter is re-armed every forward; the post-mortem words behind it (+64 B) are STICKY -- they keep the first
+    // timeout since the caller zeroed the scratch buffer, so a failure inside a long captured rollout can still be read
+    cudaError_t e = cudaMemsetAsync(base + lay.counter, 0, 64, s);
     if (e != cudaSuccess) return (int)e;
     const size_t smem = sizeof(rt::Smem) + 128 + (size_t)2 * rt::kChunks * (st->m * 128 + 2 * rt::kPad) * 16;
     static std::atomic<size_t> granted[5][kMaxDevices];

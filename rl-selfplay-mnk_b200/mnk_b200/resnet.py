@@ -197,7 +197,7 @@ class NativeResNet:
         need = int(self._L.mnk_resnet_tower_train_scratch_bytes(m, n, num_envs, self.blocks))
         check(need if need < 0 else 0, "mnk_resnet_tower_train_scratch_bytes")
         if self._scratch is None or self._scratch.numel() < need:
-            self._scratch = torch.empty(need, dtype=torch.uint8, device=self._dev)
+            self._scratch = torch.zeros(need, dtype=torch.uint8, device=self._dev)    # (zeroed: sticky post-mortem words)
         return self._scratch
 
     def pointer_signature(self):

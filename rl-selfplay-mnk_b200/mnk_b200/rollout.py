@@ -309,8 +309,11 @@ class RolloutCollector:
         flags = [o._err for o in (network, getattr(vec_env.opponent_policy, "net", None)) if hasattr(o, "_err")]
         tot = torch.cat([totals] + [f.double() for f in flags]).tolist()
         if any(v != 0.0 for v in tot[6:]):
-            raise RuntimeError("mnk_b200: a tcgen05 tower launch of this rollout hit an internal barrier timeout; "
-                               "its features (and everything sampled from them) are invalid")
+            who = ["agent network", "opponent network"]
+            codes = ", ".join(f"{w} flag {int(v):#x}" for w, v in zip(who, tot[6:]))
+            raise RuntimeError("mnk_b200: a tcgen05 launch of this rollout hit an internal barrier timeout; its features (and "
+                               f"everything sampled from them) are invalid [{codes}; 0x1 tower, 0x2 heads, 0x1LL weights / "
+                               "0x2LL commit watcher / 0x4LL operand TMA of train-mode layer LL]")
         elapsed = time.time() - start
         agent_steps = steps * self.num_envs * self.world_size
         episodes = tot[0]

@@ -3,7 +3,7 @@
 (CTA, step, layer, raw commit barriers) are read back from the scratch buffer."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "rl-selfplay-mnk_b200")); sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "rl-selfplay-mnk_b200")); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import torch
 from mnk_b200 import NativeResNet, ResNetActorCritic, TorchVectorMnkEnv, _lib
 if os.environ.get("MNK_LIB"):
@@ -30,12 +30,9 @@ for rep in range(reps):
     if code or rep < 2 or rep == reps - 1:
         print(f"envs={ne} forward {rep}: {ms:.2f} ms code {hex(code)}", flush=True)
     if code:
-        need = int(_lib.lib().mnk_resnet_tower_train_scratch_bytes(m, n, ne, native.blocks))
-        pm = native._scratch[need - 256 + 64: need - 256 + 128].view(torch.int32).tolist()
-        tot = (pm[1] >> 16) & 0xFFFF
-        print(f"    first watcher timeout of this forward: cta {pm[1] & 0xFFFF}, {tot} steps, watcher at step {pm[2] & 0xFFFF} "
-              f"(total-{tot - (pm[2] & 0xFFFF)}), layer {pm[2] >> 16}; commit barriers " +
-              " ".join(hex(((pm[5 + 2 * q] & 0xFFFFFFFF) << 32) | (pm[4 + 2 * q] & 0xFFFFFFFF)) for q in range(5)), flush=True)
+        import _postmortem
+        print(_postmortem.describe(_postmortem.read(native, _lib.lib(), m, n, ne), m), flush=True)
+        native._scratch.zero_()
         native._err.zero_()
     if bad >= int(os.environ.get("MAX_BAD", 3)):
         break
