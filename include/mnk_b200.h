@@ -261,6 +261,22 @@ int mnk_resnet_tower(const mnk_state_t* st, const uint8_t* swap, const void* wei
                      const float* head_w, const float* head_b, int32_t blocks, float* policy_feat,
                      float* value_feat, int32_t* error, void* stream);
 
+/* The convolutional body of the reference's wider networks (configs.py:36-65), eval-mode BatchNorm folded, one tcgen05
+ * kernel reading the packed bitboards (csrc/mnk_convtower.cu):
+ *   residual = 1: BaseResNetActorCritic.forward_body (resnet.py:68-71) -- layer 0 = conv_in, then (conv1, conv2 + skip)
+ *                 pairs; `layers` = 1 + 2 * num_blocks.  "resnet_b_l": channels = 80, layers = 11
+ *   residual = 0: BaseCnnActorCritic.shared_body (cnn.py:12-29) -- a plain conv3x3 + BN + ReLU stack.
+ *                 "cnn_b_s": 56 channels zero-padded to channels = 64, layers = 4; "cnn_b_l": channels = 96, layers = 8
+ * followed by the 1x1 convolutions that open the two heads.  channels must be 64, 80 or 96 (MNK_ERR_ARG otherwise);
+ * boards up to n <= 22 whose guard-strided env (m (n+1) + n + 2 pixel rows) fits the CTA tile of 512 (384 at 96
+ * channels) pixel rows, MNK_ERR_GEOM otherwise.
+ *   weights  op16 [layers][9 taps][channels/8 k-chunks][channels c_out][8 c_in]  (tap = ky*3+kx; 16-byte aligned)
+ *   bias     f32  [layers][channels] (16-byte aligned)   head_w f32 [3][channels], head_b f32 [3]
+ *   policy_feat / value_feat / error as mnk_resnet_tower (error flag value 4) */
+int mnk_conv_tower(const mnk_state_t* st, const uint8_t* swap, int32_t channels, int32_t layers, int32_t residual,
+                   const void* weights, const float* bias, const float* head_w, const float* head_b,
+                   float* policy_feat, float* value_feat, int32_t* error, void* stream);
+
 /* The same tower for boards with 3 <= m <= 10 rows (MNK_ERR_GEOM otherwise), with the three vertical taps fused
  * into the MMA's N dimension (csrc/mnk_resnet_rows.cu): identical arguments and results, except the weight layout
  *   weights_rows  op16 [1+2*blocks][3 kx][4 k-chunks][ky*32 + c_out][8 c_in]   (16-byte aligned)

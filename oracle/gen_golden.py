@@ -317,6 +317,63 @@ def gen_resnet(seed, m, n, k, batch):
     return out
 
 
+def gen_widenet(arch, seed, m, n, k, batch):
+    """Eval-mode forward of the reference's wider convolutional networks (configs.py:36-65: "resnet_b_l" = 80 channels x
+    5 residual blocks, "cnn_b_s" = [56] * 4, "cnn_b_l" = [96] * 8) with randomised weights and BatchNorm statistics.
+    The conv / linear weights are rounded to fp16-representable values first so that the fixture can store them as fp16
+    (half the size) and still hold EXACTLY the parameters the recorded outputs were computed with."""
+    import importlib
+    cfg = importlib.import_module("alg.architectures.configs")
+    cls = {"resnet_b_l": cfg.ResNetLActorCritic, "cnn_b_s": cfg.CnnSActorCritic, "cnn_b_l": cfg.CnnLActorCritic}[arch]
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    net = cls((2, m, n), m * n)
+    actor = net.policy_head if hasattr(net, "policy_head") else net.actor
+    with torch.no_grad():
+        for mod in net.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.3)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.7, 1.3)
+                mod.bias.normal_(0, 0.2)
+            elif isinstance(mod, (torch.nn.Conv2d, torch.nn.Linear)):
+                mod.bias.normal_(0, 0.1)
+            elif isinstance(mod, torch.nn.LayerNorm):
+                mod.weight.uniform_(0.8, 1.2)
+                mod.bias.normal_(0, 0.1)
+        actor[7].weight.mul_(60.0)                   # (gain 0.01 at initialisation: scale the logits up, as in gen_resnet)
+        for mod in net.modules():
+            if isinstance(mod, (torch.nn.Conv2d, torch.nn.Linear)):
+                mod.weight.copy_(mod.weight.half().float())
+    net.eval()
+    env = TorchVectorMnkEnv(m, n, k, batch, device="cpu")
+    obs = env.reset()
+    depth = rng.integers(0, m * n - 1, size=batch)
+    for t in range(m * n - 1):
+        a = RandomPolicy(m * n).act(obs)
+        idx = torch.from_numpy(np.nonzero(depth > t)[0])
+        if len(idx) == 0:
+            break
+        obs, _, _ = env.step_subset(a[idx], idx)
+    x = obs["observation"].clone()
+    flip = torch.from_numpy(rng.random(batch) < 0.5)
+    x[flip] = torch.flip(x[flip], dims=(1,))
+    mask = obs["action_mask"].clone()
+    mask[0] = False                                 # an all-masked row
+    with torch.no_grad():
+        dist, value = net(x, mask)
+    out = {}
+    for key, v in net.state_dict().items():
+        half = key.endswith(".weight") and v.dim() >= 2
+        out[f"param/{key}"] = v.numpy().astype(np.float16) if half else v.numpy()
+    out.update(geom=np.array([m, n, k, batch]), obs=pack(x.numpy()), mask=pack(mask.numpy()), logits=dist.logits.numpy(),
+               value=value.numpy(), arch=np.array(arch))
+    return out
+
+
+WIDENETS = [("resnet_b_l", 31, 9, 9, 5, 40), ("cnn_b_s", 32, 9, 9, 5, 40), ("cnn_b_l", 33, 7, 7, 4, 24)]
+
+
 def gen_resnet_train(seed, m, n, k, batch):
     """TRAIN-mode forward of the same network, as PPOAgent.learn's rollout runs it (src/alg/ppo.py:97: the module is
     never switched to eval there): BatchNorm uses the statistics of this batch and updates its running buffers.
@@ -340,6 +397,10 @@ def gen_resnet_train(seed, m, n, k, batch):
 
 
 def main():
+    if "--widenet-only" in sys.argv:
+        for arch, seed, m, n, k, batch in WIDENETS:
+            np.savez_compressed(os.path.join(OUT, f"widenet_{arch}_{m}x{n}.npz"), **gen_widenet(arch, seed, m, n, k, batch))
+        return
     if "--resnet-train-only" in sys.argv:
         np.savez_compressed(os.path.join(OUT, "resnet_train_b_s_9x9.npz"), **gen_resnet_train(21, 9, 9, 5, 96))
         np.savez_compressed(os.path.join(OUT, "resnet_train_b_s_7x7.npz"), **gen_resnet_train(22, 7, 7, 4, 40))
@@ -365,6 +426,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "resnet_b_s_13x13.npz"), **gen_resnet(12, 13, 13, 5, 24))
     np.savez_compressed(os.path.join(OUT, "resnet_train_b_s_9x9.npz"), **gen_resnet_train(21, 9, 9, 5, 96))
     np.savez_compressed(os.path.join(OUT, "resnet_train_b_s_7x7.npz"), **gen_resnet_train(22, 7, 7, 4, 40))
+    for arch, seed, m, n, k, batch in WIDENETS:
+        np.savez_compressed(os.path.join(OUT, f"widenet_{arch}_{m}x{n}.npz"), **gen_widenet(arch, seed, m, n, k, batch))
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} fixtures, {total / 1024:.1f} KiB -> {os.path.normpath(OUT)}")
 

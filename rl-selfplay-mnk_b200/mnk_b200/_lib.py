@@ -133,6 +133,7 @@ SIGNATURES = {
     "mnk_episode_stats": (_I32, [_VP, _VP, _I64, _VP, _VP, _VP, _VP]),
     "mnk_resnet_operand_dtype": (_I32, []),
     "mnk_resnet_tower": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
+    "mnk_conv_tower": (_I32, [_ST, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mnk_resnet_tower_rows": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "mnk_resnet_tower_train_scratch_bytes": (_I64, [_I32, _I32, _I64, _I32]),
     "mnk_resnet_tower_train": (_I32, [_ST, _VP, _VP, ctypes.POINTER(MnkBnTrain), _VP, _VP, _I32, _VP, _I64, _VP, _VP, _VP, _VP]),

@@ -7,9 +7,9 @@ The reference writes ``<dir>/model_00042.pt`` (a plain ``state_dict``) next to `
 ``ResNetActorCritic`` keeps the reference's parameter names, and keys saved from a
 ``torch.compile``-wrapped module (``_orig_mod.`` prefix, model_export.py:167-174) are accepted.
 
-Only ``resnet_b_s`` is constructed here -- it is the network of the accelerated path
-(DESIGN.md section 7); other architecture names raise, so a caller falls back to the reference's
-own loader for them rather than silently getting a different network.
+The convolutional families are constructed here (``mnk_b200.nets.ARCHITECTURES``: resnet_b_s -- the network of the
+accelerated path -- resnet_b_l, cnn_b_s, cnn_b_l and the older resnet_s / resnet_l / cnn_s / cnn_l); the transformer names
+raise, so a caller falls back to the reference's own loader for them rather than silently getting a different network.
 """
 from __future__ import annotations
 
@@ -20,9 +20,9 @@ from typing import Any, Dict, List, Optional
 
 import torch
 
-from .nets import ResNetActorCritic
+from .nets import ARCHITECTURES, build_architecture
 
-ARCHITECTURE = "resnet_b_s"
+ARCHITECTURE = "resnet_b_s"            # the default network (src/train.py)
 _COMPILED_PREFIX = "_orig_mod."
 
 
@@ -60,16 +60,16 @@ def strip_compiled_prefix(state_dict: Dict[str, torch.Tensor]) -> Dict[str, torc
     return {(k[len(_COMPILED_PREFIX):] if k.startswith(_COMPILED_PREFIX) else k): v for k, v in state_dict.items()}
 
 
-def load_model(model_dir: str, model_id: str, device: str = "cpu") -> ResNetActorCritic:
-    """``load_any_model`` (model_export.py:146-178) for resnet_b_s: eval-mode module on ``device``."""
+def load_model(model_dir: str, model_id: str, device: str = "cpu") -> torch.nn.Module:
+    """``load_any_model`` (model_export.py:146-178) for the convolutional architectures: eval-mode module on ``device``."""
     meta = read_metadata(model_dir, model_id)
     arch = meta.get("architecture", {})
-    if arch.get("name") != ARCHITECTURE:
-        raise ValueError(f"Unknown architecture: {arch.get('name')}. Known architectures: {ARCHITECTURE}")
+    if arch.get("name") not in ARCHITECTURES:
+        raise ValueError(f"Unknown architecture: {arch.get('name')}. Known architectures: {', '.join(sorted(ARCHITECTURES))}")
     weights = os.path.join(model_dir, f"{model_id}.pt")
     if not os.path.exists(weights):
         raise FileNotFoundError(f"Model weights {model_id} not found in {model_dir}")
-    model = ResNetActorCritic(**arch.get("params", {}))
+    model = build_architecture(arch["name"], **arch.get("params", {}))
     model.load_state_dict(strip_compiled_prefix(torch.load(weights, map_location=device)))
     return model.to(device).eval()
 

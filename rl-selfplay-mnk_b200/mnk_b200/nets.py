@@ -1,11 +1,16 @@
-"""The residual policy/value network of the reference ("resnet_b_s": 32 channels, 4 blocks, head
-width 128; src/alg/architectures/resnet.py:8-95, configs.py:28-35) as a stock-PyTorch module with the
-reference's parameter names, so that its ``state_dict`` files load unchanged
-(``conv_in.0.weight``, ``res_blocks.N.conv1.weight``, ``policy_head.4.weight`` ...).
+"""The convolutional policy/value networks of the reference as stock-PyTorch modules with the reference's
+parameter names, so that its ``state_dict`` files load unchanged:
 
-This module is the *learner-side* network (train-mode BatchNorm, autograd) and the fp32 yardstick
-for the tcgen05 forward in ``mnk_b200.resnet``; its forward returns a ``MaskedCategorical`` whose
-sample / log_prob / entropy run on the warp-per-row sampler.
+* ``ResNetActorCritic`` -- src/alg/architectures/resnet.py:8-95 (``conv_in.0.weight``, ``res_blocks.N.conv1.weight``,
+  ``policy_head.4.weight`` ...): "resnet_b_s" (32 channels, 4 blocks, head width 128; configs.py:28-35, the default
+  network) and "resnet_b_l" (80 channels, 5 blocks, head width 256; configs.py:38-45);
+* ``CnnActorCritic`` -- src/alg/architectures/cnn.py:7-80 (``shared_body.N``, ``actor``, ``critic``): "cnn_b_s"
+  ([56] * 4, head width 128) and "cnn_b_l" ([96] * 8, head width 256; configs.py:49-65).
+
+``build_architecture(name, obs_shape, action_dim)`` constructs them by the reference's registry names.  These modules
+are the *learner-side* networks (train-mode BatchNorm, autograd) and the fp32 yardsticks for the tcgen05 forwards in
+``mnk_b200.resnet`` / ``mnk_b200.convnet``; their forward returns a ``MaskedCategorical`` whose sample / log_prob /
+entropy run on the warp-per-row sampler.
 """
 from __future__ import annotations
 
@@ -37,6 +42,19 @@ def _head(in_features: int, hidden: int, out_features: int, conv_out: int, chann
     return nn.Sequential(*layers)
 
 
+def _init_actor_critic(module: nn.Module, actor_last: nn.Linear, critic_last: nn.Linear):
+    gain = nn.init.calculate_gain("relu")
+    for mod in module.modules():
+        if isinstance(mod, (nn.Conv2d, nn.Linear)):
+            nn.init.orthogonal_(mod.weight, gain=gain)
+            nn.init.zeros_(mod.bias)
+        elif isinstance(mod, (nn.BatchNorm2d, nn.LayerNorm)):
+            nn.init.ones_(mod.weight)
+            nn.init.zeros_(mod.bias)
+    nn.init.orthogonal_(actor_last.weight, gain=0.01)
+    nn.init.orthogonal_(critic_last.weight, gain=1.0)
+
+
 class ResNetActorCritic(nn.Module):
     def __init__(self, obs_shape, action_dim, channels: int = 32, num_blocks: int = 4, head_hidden_dim: int = 128):
         super().__init__()
@@ -50,22 +68,15 @@ class ResNetActorCritic(nn.Module):
         self.policy_head = _head(2 * m * n, head_hidden_dim, action_dim, 2, channels)
         self.value_head = _head(m * n, head_hidden_dim, 1, 1, channels, final=nn.Tanh())
         self._init_weights()
-        self._architecture_name = "resnet_b_s"
+        self._architecture_name = {(32, 4, 128): "resnet_b_s", (80, 5, 256): "resnet_b_l", (64, 4, 256): "resnet_s",
+                                   (128, 8, 256): "resnet_l"}.get(
+            (channels, num_blocks, head_hidden_dim), f"resnet_{channels}x{num_blocks}_{head_hidden_dim}")
         self._architecture_params = {"obs_shape": list(self.obs_shape), "action_dim": self.action_dim}
 
     def _init_weights(self):
         """Orthogonal(relu gain) for conv / linear, unit norms, 0.01 / 1.0 gains on the last actor /
         critic layers -- the scheme of the reference's src/alg/weight_init.py:16-67."""
-        gain = nn.init.calculate_gain("relu")
-        for mod in self.modules():
-            if isinstance(mod, (nn.Conv2d, nn.Linear)):
-                nn.init.orthogonal_(mod.weight, gain=gain)
-                nn.init.zeros_(mod.bias)
-            elif isinstance(mod, (nn.BatchNorm2d, nn.LayerNorm)):
-                nn.init.ones_(mod.weight)
-                nn.init.zeros_(mod.bias)
-        nn.init.orthogonal_(self.policy_head[7].weight, gain=0.01)
-        nn.init.orthogonal_(self.value_head[7].weight, gain=1.0)
+        _init_actor_critic(self, self.policy_head[7], self.value_head[7])
 
     def forward_body(self, x):
         return self.res_blocks(self.conv_in(x))
@@ -77,3 +88,58 @@ class ResNetActorCritic(nn.Module):
         if action_mask is not None and action_mask.dim() == 1 and logits.dim() == 2:
             action_mask = action_mask.unsqueeze(0)
         return MaskedCategorical(logits, action_mask), value
+
+
+class CnnActorCritic(nn.Module):
+    """BaseCnnActorCritic (src/alg/architectures/cnn.py:7-80): a stack of conv3x3 + BatchNorm + ReLU, then the same two
+    heads as the residual network under the names ``actor`` / ``critic``."""
+
+    def __init__(self, obs_shape, action_dim, channels=(56, 56, 56, 56), head_hidden_dim: int = 128):
+        super().__init__()
+        self.obs_shape = tuple(int(x) for x in obs_shape)
+        self.action_dim = int(action_dim)
+        self.channels = tuple(int(c) for c in channels)
+        _, m, n = self.obs_shape
+        layers, c_in = [], self.obs_shape[0]
+        for c_out in self.channels:
+            layers += [nn.Conv2d(c_in, c_out, kernel_size=3, padding=1), nn.BatchNorm2d(c_out), nn.ReLU()]
+            c_in = c_out
+        self.shared_body = nn.Sequential(*layers)
+        self.actor = _head(2 * m * n, head_hidden_dim, action_dim, 2, c_in)
+        self.critic = _head(m * n, head_hidden_dim, 1, 1, c_in, final=nn.Tanh())
+        _init_actor_critic(self, self.actor[7], self.critic[7])
+        self._architecture_name = {((56,) * 4, 128): "cnn_b_s", ((96,) * 8, 256): "cnn_b_l", ((64,) * 4, 256): "cnn_s",
+                                   ((192,) * 6, 256): "cnn_l"}.get(
+            (self.channels, head_hidden_dim), f"cnn_{'_'.join(map(str, self.channels))}_{head_hidden_dim}")
+        self._architecture_params = {"obs_shape": list(self.obs_shape), "action_dim": self.action_dim}
+
+    def forward_body(self, x):
+        return self.shared_body(x)
+
+    def forward(self, obs, action_mask=None):
+        features = self.shared_body(obs)
+        logits = self.actor(features)
+        value = self.critic(features)
+        if action_mask is not None and action_mask.dim() == 1 and logits.dim() == 2:
+            action_mask = action_mask.unsqueeze(0)
+        return MaskedCategorical(logits, action_mask), value
+
+
+# the reference's registry names (src/utils/model_export.py:17-35) for the convolutional families
+ARCHITECTURES = {
+    "resnet_b_s": lambda obs_shape, action_dim: ResNetActorCritic(obs_shape, action_dim, 32, 4, 128),
+    "resnet_b_l": lambda obs_shape, action_dim: ResNetActorCritic(obs_shape, action_dim, 80, 5, 256),
+    "cnn_b_s": lambda obs_shape, action_dim: CnnActorCritic(obs_shape, action_dim, (56,) * 4, 128),
+    "cnn_b_l": lambda obs_shape, action_dim: CnnActorCritic(obs_shape, action_dim, (96,) * 8, 256),
+    # the older, non-"_b_" entries of the same registry (resnet.py:96-112, cnn.py:82-109)
+    "resnet_s": lambda obs_shape, action_dim: ResNetActorCritic(obs_shape, action_dim, 64, 4, 256),
+    "resnet_l": lambda obs_shape, action_dim: ResNetActorCritic(obs_shape, action_dim, 128, 8, 256),
+    "cnn_s": lambda obs_shape, action_dim: CnnActorCritic(obs_shape, action_dim, (64,) * 4, 256),
+    "cnn_l": lambda obs_shape, action_dim: CnnActorCritic(obs_shape, action_dim, (192,) * 6, 256),
+}
+
+
+def build_architecture(name: str, obs_shape, action_dim) -> nn.Module:
+    if name not in ARCHITECTURES:
+        raise ValueError(f"Unknown architecture: {name}. Known architectures: {', '.join(sorted(ARCHITECTURES))}")
+    return ARCHITECTURES[name](obs_shape, action_dim)

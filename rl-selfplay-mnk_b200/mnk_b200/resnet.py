@@ -290,11 +290,13 @@ class NativeResNet:
 
 
 class NativeNNPolicy(Policy):
-    """NNPolicy (src/selfplay/policy.py:32-54) on the tcgen05 forward."""
+    """NNPolicy (src/selfplay/policy.py:32-54) on the tcgen05 forward: NativeResNet for the 32-channel default network,
+    NativeConvNet (mnk_b200.convnet) for the wider residual / plain convolutional architectures."""
 
     def __init__(self, model: nn.Module, device="cuda", seed: Optional[int] = None):
+        from .convnet import native_network
         model.eval()
-        self.net = NativeResNet(model, device=device)
+        self.net = native_network(model, device=device)
         self.seed = fresh_seed() if seed is None else seed
         self._calls = 0
         self.counter_base: Optional[torch.Tensor] = None     # see TorchSelfPlayWrapper.counter_base
