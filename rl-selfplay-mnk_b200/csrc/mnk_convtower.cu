@@ -20,8 +20,9 @@
 //   * a layer's weights are 9 x C x C x 2 B (115 KB at C = 80) -- too large to sit next to the activations -- so they
 //     stream TAP BY TAP through a three-slot ring of 1-D TMA bulk copies issued by a producer warp; a slot is handed
 //     back by the tcgen05.commit of the MMAs that read it;
-//   * 8 epilogue warps (TMEM lane quarter x channel half): bias (+ skip) + ReLU -> 16-bit back to shared memory, guard
-//     rows as zeros; the last layer applies the 1x1 head convolutions from the fp32 registers.
+//   * 16 epilogue warps (two groups on alternate M-blocks x TMEM lane quarter x channel half; the epilogue is latency-
+//     bound, 8 warps took 40 % of the layer time): bias (+ skip) + ReLU -> 16-bit back to shared memory, guard rows as
+//     zeros; the last layer applies the 1x1 head convolutions from the fp32 registers.
 // Envs per CTA at 9x9: 5 (C <= 80, four M-blocks) or 3 (C = 96, three M-blocks: shared memory).
 #include "mnk_dispatch.cuh"
 #include "mnk_umma.cuh"
@@ -31,12 +32,13 @@ using namespace mnk_umma;
 constexpr int kMargin = 24;                   // zero rows before / after the tile (>= n + 2, i.e. n <= 22)
 constexpr int kTaps = 9;
 constexpr int kWtsSlots = 3;
-constexpr int kEpiWarps = 8;
-constexpr int kMmaWarp = kEpiWarps;           // warp 8: MMA issue
-constexpr int kTmaWarp = kMmaWarp + 1;        // warp 9: weight taps
+constexpr int kEpiGroups = 2;                 // epilogue warp groups: group g takes M-blocks g, g + 2, ...
+constexpr int kEpiWarps = 8 * kEpiGroups;     // per group: TMEM lane quarter = warp & 3, channel half = (warp >> 2) & 1
+constexpr int kMmaWarp = kEpiWarps;           // warp 16: MMA issue
+constexpr int kTmaWarp = kMmaWarp + 1;        // warp 17: weight taps
 constexpr int kThreads = 32 * (kTmaWarp + 1);
 constexpr int kLayerBarrier = 1;              // named barrier: epilogue warps + MMA warp at a layer boundary
-constexpr int kHeadBarrier = 2;               // named barrier: the 8 epilogue warps (head partial sums)
+constexpr int kHeadBarrier0 = 2;              // named barriers 2, 3: the 8 warps of an epilogue group (head partial sums)
 constexpr int kTmemCols = 512;
 
 template <int C, int BM>
@@ -54,12 +56,14 @@ template <int C, int BM>
 struct Smem {
     alignas(128) unsigned char act[2][Cfg<C, BM>::kActBytes];
     alignas(128) unsigned char wts[kWtsSlots][Cfg<C, BM>::kTapBytes];
+    alignas(16) float bias[2][C];             // this layer's folded bias (double-buffered; a TMA copy per layer)
     alignas(16) float head_w[3][C];
     float head_b[4];
     float head_part[128 * BM][3];             // last layer: partial head dot products of the upper channel half
     alignas(8) unsigned long long full_bar[kWtsSlots];    // tap weights landed
     unsigned long long free_bar[kWtsSlots];               // the MMAs that read the slot have completed
     unsigned long long mma_bar;                           // all MMAs of the layer have completed
+    unsigned long long bias_bar[2];                       // the layer's bias landed
     unsigned int tmem_base;
 };
 
@@ -111,6 +115,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_kernel(Params p) {
             mbar_init(&sm.free_bar[i], 1);
         }
         mbar_init(&sm.mma_bar, 1);
+        mbar_init(&sm.bias_bar[0], 1);
+        mbar_init(&sm.bias_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kMmaWarp) {
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_kernel(Params p) {
         const u32 me = sw ? white : black, enemy = sw ? black : white;
         reinterpret_cast<uint4*>(&sm.act[0][0])[kMargin + s * p.rs + bit] = make_uint4(me * kActOne | (enemy * kActOne) << 16, 0, 0, 0);
     }
-    const int quarter = warp & 3, half = (warp >> 2) & 1;
+    const int quarter = warp & 3, half = (warp >> 2) & 1, grp = warp >> 3;
     u32 valid_bits = 0;     // which of this thread's BM pixel rows are board cells: fixed for all layers
     if (warp < kEpiWarps) {
         for (int j = 0; j < BM; ++j) {
@@ -167,6 +173,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_kernel(Params p) {
             if (elect_one()) {
                 mbar_expect_tx(&sm.full_bar[slot], K::kTapBytes);
                 tma_bulk_g2s(&sm.wts[slot][0], p.weights + (size_t)t * K::kTapBytes, K::kTapBytes, &sm.full_bar[slot]);
+                // The layer's bias rides along, into the buffer the epilogue of layer L - 2 read last.  (The epilogue first
+                // read the bias with __ldg inside its channel loop: 10 dependent L1 / L2 round trips per thread and layer,
+                // 57 % of the layer time with the tensor pipe idle -- ncu source page, profiles/README.md.)  At tap
+                // kWtsSlots of layer L the wait above has seen MMAs of THIS layer complete, so the epilogue of layer L - 1
+                // -- and with it every reader of this buffer -- is done.
+                const int L = t / kTaps;
+                if (t - L * kTaps == (L == 0 ? 0 : kWtsSlots)) {
+                    mbar_expect_tx(&sm.bias_bar[L & 1], C * 4);
+                    tma_bulk_g2s(&sm.bias[L & 1][0], p.bias + (size_t)L * C, C * 4, &sm.bias_bar[L & 1]);
+                }
             }
             __syncwarp();
         }
@@ -208,11 +224,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_kernel(Params p) {
             const int in_buf = (L & 1) ? 1 : 0, out_buf = in_buf ^ 1;
             const bool skip = p.residual != 0 && (L >= 2) && ((L & 1) == 0);
             const bool last = (L == p.layers - 1);
-            const float* bias = p.bias + (size_t)L * C + K::kHalf * half;
+            const float* bias = &sm.bias[L & 1][K::kHalf * half];
+            ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.bias_bar[L & 1], (u32)(L >> 1) & 1u)) != 0;
             ok = __all_sync(MNK_FULL_WARP, ok && mbar_wait(&sm.mma_bar, (u32)L & 1u)) != 0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int j = 0; j < BM; ++j) {
+            for (int j = grp; j < BM; j += kEpiGroups) {
                 const int i = 128 * j + quarter * 32 + lane;        // pixel row of this thread
                 const bool valid = (valid_bits >> j) & 1u;
                 const u32 keep = valid ? 0xFFFFFFFFu : 0u;
@@ -225,8 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_kernel(Params p) {
                 for (int kc = 0; kc < K::kHalf / 8; ++kc) {          // 8 channels at a time; the next load is in flight
                     tmem_wait8(acc[kc & 1]);
                     if (kc + 1 < K::kHalf / 8) tmem_ld8(taddr + 8 * (kc + 1), acc[(kc + 1) & 1]);
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * kc));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * kc) + 1);
+                    const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * kc);
+                    const float4 b1 = *(reinterpret_cast<const float4*>(bias + 8 * kc) + 1);
                     float v[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) v[ch] += __uint_as_float(acc[kc & 1][ch]);
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tower_kernel(Params p) {
                 if (last) {   // the 1x1 convolutions that open the two heads: the two channel halves meet in shared memory
                     float* part = sm.head_part[i];
                     if (half == 1) { part[0] = h0; part[1] = h1; part[2] = h2; }
-                    asm volatile("bar.sync %0, %1;" ::"r"(kHeadBarrier), "r"(32 * kEpiWarps) : "memory");
+                    asm volatile("bar.sync %0, %1;" ::"r"(kHeadBarrier0 + grp), "r"(256) : "memory");
                     if (half == 0 && valid) {
                         h0 += part[0] + sm.head_b[0];
                         h1 += part[1] + sm.head_b[1];

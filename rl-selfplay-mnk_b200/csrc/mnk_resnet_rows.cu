@@ -156,6 +156,11 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
     bool ok = true;
     const int lead = min(kLead, m);          // MMA block g waits for step g - lead (<= g - m: its input row is written too)
     const int total_steps = p.layers * m;
+#ifdef MNK_ROWS_EARLY_RELEASE   // experiment, off: 0.628 ms against 0.617 ms per 32,768 envs at 9x9 (profiles/README.md)
+    const bool early_release = (m == 6 || m >= 8);
+#else
+    const bool early_release = false;
+#endif
 #ifdef MNK_TIMELINE   // debug build only (tools/timeline_rows.py): cycle stamps of one mid-grid CTA into error[1..]
     const long long t_origin = clock64();
     const bool stamp = p.error != nullptr && blockIdx.x == gridDim.x / 2 && lane == 0;
@@ -269,6 +274,17 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
                 tmem_ld_wait(q1);
                 tmem_ld_wait(q2);
                 if ((warp % kSetWarps) == 0) MNK_STAMP(e, 3);   // TMEM slices in registers
+#ifdef MNK_ROWS_EARLY_RELEASE   // experiment, off: 0.628 ms against 0.617 ms per 32,768 envs at 9x9 (profiles/README.md)
+                // Early release: the step's TMEM slot is free as soon as its slices are in registers.  The release also
+                // tells MMA block e + lead that ITS operand row -- written by step e + lead - m -- is in shared memory; that
+                // step is an earlier step of this set (complete) when lead - m is even, and for odd m it is a step of the
+                // other set that completed before that set's release of step e - 3 only if it lies at or before e - 5:
+                // boards with m = 6 or m >= 8 rows (early_release); the others release at the end of the step.
+                if (early_release && e + lead < total_steps) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("bar.arrive %0, %1;" ::"r"(kStepBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
+                }
+#endif
                 float v[16];
 #pragma unroll
                 for (int ch = 0; ch < 16; ++ch) {
@@ -333,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_tower_rows_kernel(Params p
                     asm volatile("bar.sync %0, 256;" ::"r"(13 + set) : "memory");
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                if (e + lead < total_steps)   // the last `lead` steps have no consumer
+                if (!early_release && e + lead < total_steps)   // the last `lead` steps have no consumer
                     asm volatile("bar.arrive %0, %1;" ::"r"(kStepBarrier0 + bar), "r"(32 * (kSetWarps + 1)) : "memory");
                 if ((warp % kSetWarps) == 0) MNK_STAMP(e, 4);   // step done
             }
