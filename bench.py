@@ -773,6 +773,58 @@ def bench_rollout(ctx: Ctx, args, envs: int, agent_bn: str, extras: bool = True)
     return line
 
 
+# ------------------------------------------------------------------------------------------------
+# B200 arm: the network forwards alone (every tcgen05 forward the package ships), samples/s
+# ------------------------------------------------------------------------------------------------
+def bench_forwards(ctx: Ctx, args, envs: int):
+    """`forward_env` (tower + head tails, logits and values from the packed bitboards) of every native network at 9x9 on
+    `envs` mid-game positions per GPU: the default resnet_b_s in eval and train mode and the wider architectures of
+    src/alg/architectures/configs.py:36-65 on mnk_conv_tower.  CUDA events around 10 forwards after 3 warm-ups, max over
+    ranks; useful FLOPs = 2 * MACs of the 3x3 convolutions + the head Linear layers (what the reference network computes,
+    padding excluded) against the measured sustained bf16 peak.  Each forward streams new features (tens of MB) and the
+    towers re-read only weights, so no L2 flush is needed between iterations."""
+    torch = ctx.torch
+    from mnk_b200 import NativeResNet, TorchVectorMnkEnv, build_architecture, native_network
+    m, n, k = 9, 9, 5
+    cells = m * n
+    env = TorchVectorMnkEnv(m, n, k, envs, device=f"cuda:{ctx.local_rank}", env_offset=ctx.rank * envs)
+    env.reset()
+    for t in range(24):
+        env.step_autoreset(env.random_legal_actions(SEED, t), materialise=False)
+    peak, peak_src = measured_peak("bf16_tflops_sustained")
+    out = {}
+    for name, mode in (("resnet_b_s", "eval"), ("resnet_b_s", "train"), ("resnet_b_l", "eval"), ("cnn_b_s", "eval"), ("cnn_b_l", "eval")):
+        torch.manual_seed(0)
+        net = build_architecture(name, (2, m, n), cells).to(ctx.dev)
+        net.train(mode == "train")
+        fwd = NativeResNet(net, device=ctx.dev, bn_mode="train") if mode == "train" else native_network(net, device=ctx.dev)
+        flops = sum(2 * cells * c.in_channels * c.out_channels * c.kernel_size[0] * c.kernel_size[1]
+                    for c in net.modules() if isinstance(c, torch.nn.Conv2d))
+        flops += sum(2 * l.in_features * l.out_features for l in net.modules() if isinstance(l, torch.nn.Linear))
+        for _ in range(3):
+            fwd.forward_env(env)
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            fwd.forward_env(env)
+        e1.record()
+        ctx.barrier()
+        ms = ctx.reduce([e0.elapsed_time(e1) / reps], "max")[0]
+        fwd.check_error()
+        tf = envs * flops / (ms * 1e-3) / 1e12
+        out[f"{name}_{mode}"] = {"samples_per_s": envs * ctx.world / (ms * 1e-3), "ms_per_forward": ms, "mflop_per_sample": flops / 1e6,
+                                 "useful_tflops_per_gpu": tf, "frac_of_bf16_peak": tf / peak,
+                                 "kernel": type(fwd).__name__ + (" (mnk_resnet_tower_train)" if mode == "train" else "")}
+        del fwd, net
+    del env
+    torch.cuda.empty_cache()
+    return {"metric": "network forward samples/sec (9x9, logits + value from packed bitboards)", "unit": "samples/s", "n_gpus": ctx.world,
+            "envs_per_gpu": envs, "dtype": "fp16 operands, fp32 accumulate", "peak_tflops": peak, "peak_source": peak_src,
+            "forwards": out}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -809,10 +861,12 @@ def main():
             line = bench_env_workload(ctx, Workload("cfg2", ctx.world, args.envs), args, primary=True)
             if not args.no_secondary:
                 secondary = {}
-                for name in ("cfg3", "cfg4", "cfg5"):
+                for name in ("cfg3", "cfg4", "cfg5", "forwards"):
                     try:
                         if name == "cfg3":
                             sec = bench_rollout(ctx, args, args.rollout_envs, args.agent_bn)
+                        elif name == "forwards":
+                            sec = bench_forwards(ctx, args, args.rollout_envs)
                         else:
                             sec = bench_env_workload(ctx, Workload(name, ctx.world), args, primary=False)
                     except Exception as exc:      # a secondary line must never take the headline down with it

@@ -277,6 +277,26 @@ int mnk_conv_tower(const mnk_state_t* st, const uint8_t* swap, int32_t channels,
                    const void* weights, const float* bias, const float* head_w, const float* head_b,
                    float* policy_feat, float* value_feat, int32_t* error, void* stream);
 
+/* The body of the reference's transformer networks (src/alg/architectures/transformer.py:7-92, configs.py:7-25):
+ * cell_embed + pos_embed, `layers` pre-norm nn.TransformerEncoderLayer (ReLU, no dropout) and the two Conv1d(D, ., 1) that
+ * open the heads, one tcgen05 kernel per call reading the packed bitboards (csrc/mnk_transformer.cu).  Supported shapes:
+ * (embed_dim, heads) = (56, 4) "transformer_b_s" and (96, 8) "transformer_b_l"; boards of at most 128 cells
+ * (MNK_ERR_GEOM otherwise).  With DP = embed_dim rounded up to 16, QP = 16 * heads, F = 4 * embed_dim:
+ *   weights       op16, per layer mnk_transformer_layer_weight_bytes() bytes: B-operand tiles [K/8][N][8] in consumption
+ *                 order -- in_proj (K = DP, N = 3 QP: Q | K | V, head_dim zero-padded to 16; two N-halves at embed_dim 96),
+ *                 out_proj (K = QP, N = DP), linear1 (K = DP, N = F; two N-halves at 96), linear2 (K = F, N = DP; two
+ *                 K-halves at 96); 16-byte aligned
+ *   layer_params  f32 [layers][mnk_transformer_layer_params()]: norm1 weight, bias [DP] | in_proj bias [3 QP] | out_proj
+ *                 bias [DP] | norm2 weight, bias [DP] | linear1 bias [F] | linear2 bias [DP]  (padding = 0)
+ *   embed f32 [3][DP]: cell_embed weight of channel 0, channel 1, bias;  pos f32 [m*n][DP];  head_w f32 [3][DP], head_b f32 [3]
+ *   policy_feat f32 [num_envs][2*m*n], value_feat f32 [num_envs][m*n]; error flag value 8 */
+int64_t mnk_transformer_layer_weight_bytes(int32_t embed_dim, int32_t heads);
+int64_t mnk_transformer_layer_params(int32_t embed_dim, int32_t heads);
+int mnk_transformer_body(const mnk_state_t* st, const uint8_t* swap, int32_t embed_dim, int32_t heads, int32_t layers,
+                         const void* weights, const float* layer_params, const float* embed, const float* pos,
+                         const float* head_w, const float* head_b, float* policy_feat, float* value_feat,
+                         int32_t* error, void* stream);
+
 /* The same tower for boards with 3 <= m <= 10 rows (MNK_ERR_GEOM otherwise), with the three vertical taps fused
  * into the MMA's N dimension (csrc/mnk_resnet_rows.cu): identical arguments and results, except the weight layout
  *   weights_rows  op16 [1+2*blocks][3 kx][4 k-chunks][ky*32 + c_out][8 c_in]   (16-byte aligned)

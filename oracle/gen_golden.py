@@ -324,7 +324,8 @@ def gen_widenet(arch, seed, m, n, k, batch):
     (half the size) and still hold EXACTLY the parameters the recorded outputs were computed with."""
     import importlib
     cfg = importlib.import_module("alg.architectures.configs")
-    cls = {"resnet_b_l": cfg.ResNetLActorCritic, "cnn_b_s": cfg.CnnSActorCritic, "cnn_b_l": cfg.CnnLActorCritic}[arch]
+    cls = {"resnet_b_l": cfg.ResNetLActorCritic, "cnn_b_s": cfg.CnnSActorCritic, "cnn_b_l": cfg.CnnLActorCritic,
+           "transformer_b_s": cfg.TransformerSActorCritic, "transformer_b_l": cfg.TransformerLActorCritic}[arch]
     torch.manual_seed(seed)
     rng = np.random.default_rng(seed)
     net = cls((2, m, n), m * n)
@@ -341,10 +342,15 @@ def gen_widenet(arch, seed, m, n, k, batch):
             elif isinstance(mod, torch.nn.LayerNorm):
                 mod.weight.uniform_(0.8, 1.2)
                 mod.bias.normal_(0, 0.1)
+            elif isinstance(mod, torch.nn.MultiheadAttention):
+                mod.in_proj_bias.normal_(0, 0.1)
+        if hasattr(net, "pos_embed"):                # (initialised with std 0.02: make the embedding matter)
+            net.pos_embed.normal_(0, 0.5)
+            net.cell_embed.weight.normal_(0, 0.5)
         actor[7].weight.mul_(60.0)                   # (gain 0.01 at initialisation: scale the logits up, as in gen_resnet)
-        for mod in net.modules():
-            if isinstance(mod, (torch.nn.Conv2d, torch.nn.Linear)):
-                mod.weight.copy_(mod.weight.half().float())
+        for name, prm in net.named_parameters():     # every matrix-shaped ".weight" is stored as fp16 below
+            if name.endswith(".weight") and prm.dim() >= 2:
+                prm.copy_(prm.half().float())
     net.eval()
     env = TorchVectorMnkEnv(m, n, k, batch, device="cpu")
     obs = env.reset()
@@ -372,6 +378,7 @@ def gen_widenet(arch, seed, m, n, k, batch):
 
 
 WIDENETS = [("resnet_b_l", 31, 9, 9, 5, 40), ("cnn_b_s", 32, 9, 9, 5, 40), ("cnn_b_l", 33, 7, 7, 4, 24)]
+TRANSFORMERS = [("transformer_b_s", 41, 9, 9, 5, 40), ("transformer_b_l", 42, 7, 7, 4, 24)]
 
 
 def gen_resnet_train(seed, m, n, k, batch):
@@ -397,6 +404,10 @@ def gen_resnet_train(seed, m, n, k, batch):
 
 
 def main():
+    if "--transformer-only" in sys.argv:
+        for arch, seed, m, n, k, batch in TRANSFORMERS:
+            np.savez_compressed(os.path.join(OUT, f"widenet_{arch}_{m}x{n}.npz"), **gen_widenet(arch, seed, m, n, k, batch))
+        return
     if "--widenet-only" in sys.argv:
         for arch, seed, m, n, k, batch in WIDENETS:
             np.savez_compressed(os.path.join(OUT, f"widenet_{arch}_{m}x{n}.npz"), **gen_widenet(arch, seed, m, n, k, batch))
@@ -426,7 +437,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "resnet_b_s_13x13.npz"), **gen_resnet(12, 13, 13, 5, 24))
     np.savez_compressed(os.path.join(OUT, "resnet_train_b_s_9x9.npz"), **gen_resnet_train(21, 9, 9, 5, 96))
     np.savez_compressed(os.path.join(OUT, "resnet_train_b_s_7x7.npz"), **gen_resnet_train(22, 7, 7, 4, 40))
-    for arch, seed, m, n, k, batch in WIDENETS:
+    for arch, seed, m, n, k, batch in WIDENETS + TRANSFORMERS:
         np.savez_compressed(os.path.join(OUT, f"widenet_{arch}_{m}x{n}.npz"), **gen_widenet(arch, seed, m, n, k, batch))
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"wrote {len(os.listdir(OUT))} fixtures, {total / 1024:.1f} KiB -> {os.path.normpath(OUT)}")

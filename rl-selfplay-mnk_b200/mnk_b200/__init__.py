@@ -11,13 +11,14 @@ from .policy import NNPolicy, Policy, RandomPolicy  # noqa: F401
 from .sampling import MaskedCategorical, masked_sample  # noqa: F401
 from .wrapper import TorchSelfPlayWrapper  # noqa: F401
 from .rollout import RolloutBuffer, RolloutCollector, RolloutStats  # noqa: F401
-from .nets import CnnActorCritic, ResNetActorCritic, build_architecture  # noqa: F401
+from .nets import CnnActorCritic, ResNetActorCritic, TransformerActorCritic, build_architecture  # noqa: F401
 from .resnet import NativeNNPolicy, NativeResNet  # noqa: F401
 from .convnet import NativeConvNet, native_network  # noqa: F401
+from .transformer import NativeTransformer  # noqa: F401
 from .ppo import PPOAgent, TrainingMetrics  # noqa: F401
 from . import dist, model_io  # noqa: F401
 
 __all__ = ["build", "lib", "LIB_PATH", "TorchVectorMnkEnv", "TorchSelfPlayWrapper", "Policy", "RandomPolicy", "NNPolicy",
            "MaskedCategorical", "masked_sample", "RolloutBuffer", "RolloutCollector", "RolloutStats", "dist", "model_io",
-           "ResNetActorCritic", "CnnActorCritic", "build_architecture", "NativeResNet", "NativeConvNet", "native_network",
+           "ResNetActorCritic", "CnnActorCritic", "build_architecture", "NativeResNet", "NativeConvNet", "NativeTransformer", "TransformerActorCritic", "native_network",
            "NativeNNPolicy", "PPOAgent", "TrainingMetrics"]

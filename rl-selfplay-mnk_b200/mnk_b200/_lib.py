@@ -134,6 +134,9 @@ SIGNATURES = {
     "mnk_resnet_operand_dtype": (_I32, []),
     "mnk_resnet_tower": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "mnk_conv_tower": (_I32, [_ST, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "mnk_transformer_layer_weight_bytes": (_I64, [_I32, _I32]),
+    "mnk_transformer_layer_params": (_I64, [_I32, _I32]),
+    "mnk_transformer_body": (_I32, [_ST, _VP, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mnk_resnet_tower_rows": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     "mnk_resnet_tower_train_scratch_bytes": (_I64, [_I32, _I32, _I64, _I32]),
     "mnk_resnet_tower_train": (_I32, [_ST, _VP, _VP, ctypes.POINTER(MnkBnTrain), _VP, _VP, _I32, _VP, _I64, _VP, _VP, _VP, _VP]),

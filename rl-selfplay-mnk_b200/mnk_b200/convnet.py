@@ -6,8 +6,9 @@
 96 channels -- "resnet_b_l" (80 x 5 blocks), "cnn_b_s" (56 x 4, zero-padded to 64), "cnn_b_l" (96 x 8), "resnet_s" /
 "cnn_s" (64; configs.py:36-65, resnet.py:96-103, cnn.py:82-89) -- folds eval-mode BatchNorm into the convolutions and
 runs the whole convolutional body plus the heads' 1x1 convolutions as ONE kernel (``mnk_conv_tower``,
-csrc/mnk_convtower.cu) straight from the packed env state.  The heads' LayerNorm / Linear tails (width 128 or 256) run
-through the original torch modules (plain library GEMMs, ~1 % of the forward's FLOPs).  Inference only: NNPolicy /
+csrc/mnk_convtower.cu) straight from the packed env state.  The heads' LayerNorm / Linear tails run on ``mnk_resnet_heads_mma``
+where they have its shape (width 128, boards up to 96 cells: cnn_b_s) and through the original torch modules otherwise
+(width 256: plain library GEMMs, ~1 % of the forward's FLOPs).  Inference only: NNPolicy /
 opponent / evaluation; the 32-channel default network has its own kernels (``mnk_b200.resnet``).
 """
 from __future__ import annotations
@@ -20,7 +21,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import MnkState, check
-from .resnet import _fold, operand_dtype
+from .resnet import _fold, mma_head_params, operand_dtype, run_mma_heads
 from .sampling import MaskedCategorical
 
 KERNEL_WIDTHS = (64, 80, 96)           # channel counts mnk_conv_tower is compiled for (narrower towers are zero-padded)
@@ -63,6 +64,7 @@ class NativeConvNet:
         self._dev = dev
         self._L = _lib.lib()
         self.bn_mode = "eval"
+        self.use_mma_heads = True
         self.refresh(model)
 
     @torch.no_grad()
@@ -91,6 +93,7 @@ class NativeConvNet:
         head_b = torch.cat([ph[0].bias.detach().reshape(2), vh[0].bias.detach().reshape(1)]).float().to(dev)
         fresh = {"weights": weights.to(op).contiguous(), "bias": bias.contiguous(), "head_w": head_w.contiguous(),
                  "head_b": head_b.contiguous()}
+        fresh.update(mma_head_params(ph, vh, dev))    # tcgen05 head tails where they fit (width 128, <= 96 cells: cnn_b_s)
         old = getattr(self, "_params", None)
         if old is not None and all(old[k].shape == v.shape and old[k].dtype == v.dtype for k, v in fresh.items()):
             for k, v in fresh.items():
@@ -120,6 +123,9 @@ class NativeConvNet:
 
     @torch.no_grad()
     def tails(self, pf: torch.Tensor, vf: torch.Tensor, want_value: bool = True):
+        """Head tails: mnk_resnet_heads_mma for heads of width 128 on boards up to 96 cells, else the torch modules."""
+        if self.use_mma_heads and "hm_w2" in self._params:
+            return run_mma_heads(self._L, self._params, pf, vf, want_value, self._err, self._dev)
         return self.policy_tail(pf), (self.value_tail(vf) if want_value else None)
 
     @torch.no_grad()
@@ -158,8 +164,11 @@ class NativeConvNet:
 
 def native_network(model: nn.Module, device="cuda", **kwargs):
     """The tcgen05 forward for `model`: NativeResNet for the 32-channel default network, NativeConvNet for the wider
-    convolutional ones; raises for anything else (the transformers run through their torch modules)."""
+    convolutional ones, NativeTransformer for transformer_b_s / transformer_b_l; raises for anything else."""
     from .resnet import NativeResNet
+    from . import transformer
     if supports(model):
         return NativeConvNet(model, device=device)
+    if transformer.supports(model):
+        return transformer.NativeTransformer(model, device=device)
     return NativeResNet(model, device=device, **kwargs)

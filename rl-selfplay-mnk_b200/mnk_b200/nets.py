@@ -14,6 +14,7 @@ entropy run on the warp-per-row sampler.
 """
 from __future__ import annotations
 
+import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -125,12 +126,67 @@ class CnnActorCritic(nn.Module):
         return MaskedCategorical(logits, action_mask), value
 
 
+class TransformerActorCritic(nn.Module):
+    """BaseTransformerActorCritic (src/alg/architectures/transformer.py:7-92): a 1x1 cell embedding + learned positions,
+    pre-norm nn.TransformerEncoder layers (ReLU, feed-forward 4 x embed_dim, no dropout), Conv1d heads.  Parameter names
+    are the reference's (``cell_embed``, ``pos_embed``, ``transformer.layers.N.*``, ``policy_head``, ``value_head``)."""
+
+    def __init__(self, obs_shape, action_dim, embed_dim: int = 56, num_layers: int = 2, num_heads: int = 4,
+                 head_hidden_dim: int = 128):
+        super().__init__()
+        self.obs_shape = tuple(int(x) for x in obs_shape)
+        self.action_dim = int(action_dim)
+        c, h, w = self.obs_shape
+        tokens = h * w
+        self.embed_dim, self.num_layers, self.num_heads = embed_dim, num_layers, num_heads
+        self.cell_embed = nn.Conv2d(c, embed_dim, kernel_size=1, stride=1)
+        self.pos_embed = nn.Parameter(torch.zeros(1, tokens, embed_dim))
+        layer = nn.TransformerEncoderLayer(d_model=embed_dim, nhead=num_heads, dim_feedforward=embed_dim * 4,
+                                           batch_first=True, norm_first=True, dropout=0.0)
+        self.transformer = nn.TransformerEncoder(layer, num_layers=num_layers)
+
+        def head(conv_out, final=None):
+            layers = [nn.Conv1d(embed_dim, conv_out, kernel_size=1), nn.Flatten(), nn.LayerNorm(conv_out * tokens), nn.ReLU(),
+                      nn.Linear(conv_out * tokens, head_hidden_dim), nn.LayerNorm(head_hidden_dim), nn.ReLU(),
+                      nn.Linear(head_hidden_dim, action_dim if final is None else 1)]
+            return nn.Sequential(*(layers + ([final] if final is not None else [])))
+
+        self.policy_head = head(2)
+        self.value_head = head(1, nn.Tanh())
+        nn.init.normal_(self.pos_embed, std=0.02)            # transformer.py:53-55; the encoder keeps torch's defaults
+        nn.init.normal_(self.cell_embed.weight, mean=0.0, std=0.02)
+        nn.init.constant_(self.cell_embed.bias, 0.0)
+        for hd, last_gain in ((self.policy_head, 0.01), (self.value_head, 1.0)):      # weight_init.py:16-67 on the heads
+            for mod in hd:
+                if isinstance(mod, (nn.Conv1d, nn.Linear)):
+                    nn.init.orthogonal_(mod.weight, gain=nn.init.calculate_gain("relu"))
+                    nn.init.zeros_(mod.bias)
+            nn.init.orthogonal_(hd[7].weight, gain=last_gain)
+        self._architecture_name = {(56, 2, 4, 128): "transformer_b_s", (96, 5, 8, 256): "transformer_b_l"}.get(
+            (embed_dim, num_layers, num_heads, head_hidden_dim), f"transformer_{embed_dim}x{num_layers}x{num_heads}_{head_hidden_dim}")
+        self._architecture_params = {"obs_shape": list(self.obs_shape), "action_dim": self.action_dim}
+
+    def forward_body(self, x):
+        x = self.cell_embed(x).flatten(2).transpose(1, 2) + self.pos_embed
+        return self.transformer(x)
+
+    def forward(self, obs, action_mask=None):
+        features = self.forward_body(obs).transpose(1, 2)
+        logits = self.policy_head(features)
+        value = self.value_head(features)
+        if action_mask is not None and action_mask.dim() == 1 and logits.dim() == 2:
+            action_mask = action_mask.unsqueeze(0)
+        return MaskedCategorical(logits, action_mask), value
+
+
 # the reference's registry names (src/utils/model_export.py:17-35) for the convolutional families
 ARCHITECTURES = {
     "resnet_b_s": lambda obs_shape, action_dim: ResNetActorCritic(obs_shape, action_dim, 32, 4, 128),
     "resnet_b_l": lambda obs_shape, action_dim: ResNetActorCritic(obs_shape, action_dim, 80, 5, 256),
     "cnn_b_s": lambda obs_shape, action_dim: CnnActorCritic(obs_shape, action_dim, (56,) * 4, 128),
     "cnn_b_l": lambda obs_shape, action_dim: CnnActorCritic(obs_shape, action_dim, (96,) * 8, 256),
+    "transformer_b_s": lambda obs_shape, action_dim: TransformerActorCritic(obs_shape, action_dim, 56, 2, 4, 128),
+    "transformer_b_l": lambda obs_shape, action_dim: TransformerActorCritic(obs_shape, action_dim, 96, 5, 8, 256),
     # the older, non-"_b_" entries of the same registry (resnet.py:96-112, cnn.py:82-109)
     "resnet_s": lambda obs_shape, action_dim: ResNetActorCritic(obs_shape, action_dim, 64, 4, 256),
     "resnet_l": lambda obs_shape, action_dim: ResNetActorCritic(obs_shape, action_dim, 128, 8, 256),

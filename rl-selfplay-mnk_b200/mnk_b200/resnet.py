@@ -63,6 +63,37 @@ def _arrange_linear(w: torch.Tensor, kpad: int, npad: int) -> torch.Tensor:
 
 
 MMA_HEADS_MAX_CELLS = 96               # mnk_resnet_heads_mma (shared-memory bound); larger boards use the fp32 heads kernel
+
+
+def mma_head_params(ph: nn.Sequential, vh: nn.Sequential, dev) -> dict:
+    """Operands of mnk_resnet_heads_mma for two heads of the reference's layout (Conv2d 1x1, Flatten, LayerNorm, ReLU,
+    Linear(.., 128), LayerNorm, ReLU, Linear): the three Linear weights as UMMA B operands + one parameter vector.
+    Empty when the kernel does not cover the heads (hidden width != 128 or more than 96 cells)."""
+    cells = ph[7].out_features
+    if cells > MMA_HEADS_MAX_CELLS or ph[4].out_features != 128 or vh[4].out_features != 128:
+        return {}
+    f = lambda t: t.detach().float().to(dev).contiguous()
+    r16 = lambda v: (v + 15) // 16 * 16
+    return {
+        "hm_w1p": _arrange_linear(f(ph[4].weight), r16(2 * cells), 128),
+        "hm_w1v": _arrange_linear(f(vh[4].weight), r16(cells), 128),
+        "hm_w2": _arrange_linear(f(ph[7].weight), 128, r16(cells)),
+        "hm_params": torch.cat([f(t).reshape(-1) for t in (
+            ph[2].weight, ph[2].bias, vh[2].weight, vh[2].bias, ph[4].bias, vh[4].bias, ph[5].weight, ph[5].bias,
+            vh[5].weight, vh[5].bias, vh[7].weight, ph[7].bias, vh[7].bias)]).contiguous(),
+    }
+
+
+def run_mma_heads(L, P: dict, pf: torch.Tensor, vf: torch.Tensor, want_value: bool, err: torch.Tensor, dev):
+    rows, cells = vf.shape
+    logits = torch.empty((rows, cells), dtype=torch.float32, device=dev)
+    values = torch.empty((rows, 1), dtype=torch.float32, device=dev) if want_value else None
+    with torch.cuda.device(dev):
+        check(L.mnk_resnet_heads_mma(pf.data_ptr(), vf.data_ptr(), rows, cells, P["hm_w1p"].data_ptr(), P["hm_w1v"].data_ptr(),
+                                     P["hm_w2"].data_ptr(), P["hm_params"].data_ptr(), logits.data_ptr(),
+                                     values.data_ptr() if want_value else None, err.data_ptr(),
+                                     torch.cuda.current_stream(dev).cuda_stream), "mnk_resnet_heads_mma")
+    return logits, values
 ROWS_KERNEL_BOARD_ROWS = (3, 10)      # mnk_resnet_tower_rows: boards with 3 <= m <= 10 rows (shared-memory bound)
 
 
@@ -118,17 +149,7 @@ class NativeResNet:
             "v_ln1_w": f(vh[2].weight), "v_ln1_b": f(vh[2].bias), "v_w1t": f(vh[4].weight.t()), "v_b1": f(vh[4].bias),
             "v_ln2_w": f(vh[5].weight), "v_ln2_b": f(vh[5].bias), "v_w2": f(vh[7].weight.reshape(-1)), "v_b2": f(vh[7].bias),
         }
-        cells_h = ph[7].out_features
-        if cells_h <= MMA_HEADS_MAX_CELLS:   # tcgen05 heads: the three Linear weights as UMMA B operands + one parameter vector
-            r16 = lambda v: (v + 15) // 16 * 16
-            fresh.update({
-                "hm_w1p": _arrange_linear(f(ph[4].weight), r16(2 * cells_h), 128),
-                "hm_w1v": _arrange_linear(f(vh[4].weight), r16(cells_h), 128),
-                "hm_w2": _arrange_linear(f(ph[7].weight), 128, r16(cells_h)),
-                "hm_params": torch.cat([f(t).reshape(-1) for t in (
-                    ph[2].weight, ph[2].bias, vh[2].weight, vh[2].bias, ph[4].bias, vh[4].bias, ph[5].weight, ph[5].bias,
-                    vh[5].weight, vh[5].bias, vh[7].weight, ph[7].bias, vh[7].bias)]).contiguous(),
-            })
+        fresh.update(mma_head_params(ph, vh, dev))    # tcgen05 heads where the board fits
         if self.bn_mode == "train":          # unfolded conv weights + BatchNorm parameters / running statistics, [L][32]
             bns = [b for _, b in convs]
             if any(b.momentum != bns[0].momentum or b.eps != bns[0].eps or not b.track_running_stats for b in bns):
@@ -210,18 +231,11 @@ class NativeResNet:
         """logits f32[N, A], value f32[N, 1] (None when `want_value` is False) from the tower's head features."""
         if self.torch_heads:
             return self.policy_tail(pf), (self.value_tail(vf) if want_value else None)
+        if self.use_mma_heads and "hm_w2" in self._params:
+            return run_mma_heads(self._L, self._params, pf, vf, want_value, self._err, self._dev)
         rows, cells = vf.shape
         logits = torch.empty((rows, cells), dtype=torch.float32, device=self._dev)
         values = torch.empty((rows, 1), dtype=torch.float32, device=self._dev) if want_value else None
-        if self.use_mma_heads and "hm_w2" in self._params:
-            P = self._params
-            with torch.cuda.device(self._dev):
-                check(self._L.mnk_resnet_heads_mma(pf.data_ptr(), vf.data_ptr(), rows, cells, P["hm_w1p"].data_ptr(),
-                                                    P["hm_w1v"].data_ptr(), P["hm_w2"].data_ptr(), P["hm_params"].data_ptr(),
-                                                    logits.data_ptr(), values.data_ptr() if want_value else None,
-                                                    self._err.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream),
-                      "mnk_resnet_heads_mma")
-            return logits, values
         with torch.cuda.device(self._dev):
             check(self._L.mnk_resnet_heads(pf.data_ptr(), vf.data_ptr(), rows, cells, ctypes.byref(self._heads),
                                             logits.data_ptr(), values.data_ptr() if want_value else None,

@@ -38,7 +38,8 @@ def test_module_matches_reference_network(path):
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="reference not mounted (GPU box)")
-@pytest.mark.parametrize("name", ["resnet_b_s", "resnet_b_l", "cnn_b_s", "cnn_b_l", "resnet_s", "cnn_s"])
+@pytest.mark.parametrize("name", ["resnet_b_s", "resnet_b_l", "cnn_b_s", "cnn_b_l", "resnet_s", "cnn_s", "transformer_b_s",
+                                  "transformer_b_l"])
 def test_registry_matches_live_reference(name):
     """Every registry entry against the reference's own ARCHITECTURE_REGISTRY (src/utils/model_export.py:28-47): the same
     parameter names / shapes and, with the reference's weights loaded, the same outputs."""

@@ -18,11 +18,11 @@ DEV = "cuda"
 
 @pytest.mark.parametrize("path", gio.files("widenet_"), ids=gio.name)
 def test_native_forward_matches_reference(path):
-    from mnk_b200 import NativeConvNet
+    from mnk_b200 import native_network
     from mnk_b200.resnet import operand_dtype
     g = gio.load(path)
     net, m, n, batch = load_wide(g)
-    native = NativeConvNet(net.to(DEV), device=DEV)
+    native = native_network(net.to(DEV), device=DEV)       # NativeConvNet / NativeTransformer by the module's layout
     obs = torch.from_numpy(gio.unpack(g["obs"], (2, m, n)).astype(np.float32)).to(DEV)
     mask = torch.from_numpy(gio.unpack(g["mask"], (m * n,))).to(DEV)
     dist, value = native(obs, mask)
@@ -124,3 +124,54 @@ def test_native_policy_on_wide_network_plays_legal_moves():
         obs, r, term, trunc, _ = wr.step(act)
     opp.net.check_error()
     assert bool(((r == 0) | (r == 1) | (r == -1)).all())
+
+
+@pytest.mark.parametrize("arch,m,n,k", [("transformer_b_s", 9, 9, 5), ("transformer_b_s", 3, 3, 3), ("transformer_b_s", 7, 7, 4),
+                                         ("transformer_b_s", 10, 10, 5), ("transformer_b_s", 8, 16, 5), ("transformer_b_l", 9, 9, 5),
+                                         ("transformer_b_l", 5, 7, 4), ("transformer_b_l", 11, 11, 5)], ids=str)
+def test_transformer_features_match_fp32_module_from_bitboards(arch, m, n, k):
+    """mnk_transformer_body straight from the env's bitboards against the torch fp32 module: one to fourteen boards per
+    CTA (block-diagonal attention mask), partial last CTAs, boards that fill all 128 token rows (8x16), the plane swap."""
+    from mnk_b200 import NativeTransformer, TorchVectorMnkEnv, build_architecture, native_network
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(6)
+    net = build_architecture(arch, (2, m, n), m * n).to(DEV).eval()
+    with torch.no_grad():
+        net.pos_embed.normal_(0, 0.5)
+        net.cell_embed.weight.normal_(0, 0.5)
+        for l in net.transformer.layers:
+            l.self_attn.in_proj_bias.normal_(0, 0.1)
+            l.norm1.weight.uniform_(0.8, 1.2), l.norm2.bias.normal_(0, 0.1)
+    native = native_network(net, device=DEV)
+    assert isinstance(native, NativeTransformer)
+    per_cta = 128 // (m * n)
+    for ne in (1, per_cta, per_cta + 1, 3 * per_cta - 1, 301):
+        env = TorchVectorMnkEnv(m, n, k, ne, device=DEV)
+        env.reset()
+        for t in range(m * n // 2):
+            env.step_autoreset(env.random_legal_actions(5, t), materialise=False)
+        swap = (torch.arange(ne, device=DEV) % 3 == 0).to(torch.uint8)
+        pf, vf = native.features(env._st, ne, m * n, swap)
+        native.check_error()
+        obs = env.observe()["observation"]
+        obs = torch.where(swap.bool()[:, None, None, None], obs.flip(1), obs)
+        with torch.no_grad():
+            body = net.forward_body(obs).transpose(1, 2)
+            want_pf, want_vf = net.policy_head[1](net.policy_head[0](body)), net.value_head[1](net.value_head[0](body))
+        for got, want in ((pf, want_pf), (vf, want_vf)):
+            scale = float(want.abs().max())
+            assert float((got - want).abs().max()) <= 3e-3 * scale + 1e-4, (arch, m, n, ne, float((got - want).abs().max()), scale)
+        logits, values = native.forward_env(env, swap)
+        with torch.no_grad():
+            d, v = net(obs, None)
+        assert float((logits - d._raw).abs().max()) <= 3e-3 * float(d._raw.abs().max()) + 1e-4
+        assert float((values - v).abs().max()) <= 5e-3
+
+
+def test_transformer_unsupported_shapes_raise():
+    from mnk_b200 import NativeTransformer, TransformerActorCritic, build_architecture
+    with pytest.raises(ValueError):
+        NativeTransformer(TransformerActorCritic((2, 9, 9), 81, embed_dim=64, num_layers=2, num_heads=4).to(DEV))
+    with pytest.raises(ValueError):
+        NativeTransformer(build_architecture("transformer_b_s", (2, 13, 13), 169).to(DEV))      # 169 tokens > 128
