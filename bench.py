@@ -778,10 +778,10 @@ def bench_rollout(ctx: Ctx, args, envs: int, agent_bn: str, extras: bool = True)
 # ------------------------------------------------------------------------------------------------
 def bench_forwards(ctx: Ctx, args, envs: int):
     """`forward_env` (tower + head tails, logits and values from the packed bitboards) of every native network at 9x9 on
-    `envs` mid-game positions per GPU: the default resnet_b_s in eval and train mode and the wider architectures of
-    src/alg/architectures/configs.py:36-65 on mnk_conv_tower.  CUDA events around 10 forwards after 3 warm-ups, max over
-    ranks; useful FLOPs = 2 * MACs of the 3x3 convolutions + the head Linear layers (what the reference network computes,
-    padding excluded) against the measured sustained bf16 peak.  Each forward streams new features (tens of MB) and the
+    `envs` mid-game positions per GPU: the default resnet_b_s in eval and train mode, the wider convolutional architectures of
+    src/alg/architectures/configs.py:36-65 on mnk_conv_tower and the transformers of :7-25 on mnk_transformer_body.  CUDA
+    events around 10 forwards after 3 warm-ups, max over ranks; useful FLOPs = 2 * MACs of the convolutions, the head Linear
+    layers and the encoder's matmuls (what the reference network computes, padding excluded) against the measured sustained bf16 peak.  Each forward streams new features (tens of MB) and the
     towers re-read only weights, so no L2 flush is needed between iterations."""
     torch = ctx.torch
     from mnk_b200 import NativeResNet, TorchVectorMnkEnv, build_architecture, native_network
@@ -793,14 +793,19 @@ def bench_forwards(ctx: Ctx, args, envs: int):
         env.step_autoreset(env.random_legal_actions(SEED, t), materialise=False)
     peak, peak_src = measured_peak("bf16_tflops_sustained")
     out = {}
-    for name, mode in (("resnet_b_s", "eval"), ("resnet_b_s", "train"), ("resnet_b_l", "eval"), ("cnn_b_s", "eval"), ("cnn_b_l", "eval")):
+    for name, mode in (("resnet_b_s", "eval"), ("resnet_b_s", "train"), ("resnet_b_l", "eval"), ("cnn_b_s", "eval"), ("cnn_b_l", "eval"),
+                       ("transformer_b_s", "eval"), ("transformer_b_l", "eval")):
         torch.manual_seed(0)
         net = build_architecture(name, (2, m, n), cells).to(ctx.dev)
         net.train(mode == "train")
         fwd = NativeResNet(net, device=ctx.dev, bn_mode="train") if mode == "train" else native_network(net, device=ctx.dev)
         flops = sum(2 * cells * c.in_channels * c.out_channels * c.kernel_size[0] * c.kernel_size[1]
                     for c in net.modules() if isinstance(c, torch.nn.Conv2d))
-        flops += sum(2 * l.in_features * l.out_features for l in net.modules() if isinstance(l, torch.nn.Linear))
+        heads = [getattr(net, a) for a in ("policy_head", "value_head", "actor", "critic") if hasattr(net, a)]
+        flops += sum(2 * l.in_features * l.out_features for hd in heads for l in hd if isinstance(l, torch.nn.Linear))
+        if hasattr(net, "transformer"):     # per token and layer: in_proj + out_proj + feed-forward = 12 D^2 MACs, QK^T + PV = 2 T D
+            Dm = net.embed_dim
+            flops += net.num_layers * (2 * cells * 12 * Dm * Dm + 2 * 2 * cells * cells * Dm) + 2 * cells * 3 * Dm
         for _ in range(3):
             fwd.forward_env(env)
         ctx.barrier()

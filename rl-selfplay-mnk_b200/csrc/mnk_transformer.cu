@@ -15,8 +15,9 @@
 //     zero-padded to 16), per head S = Q K^T (N = 128 keys, K = 16) and O = P V (N = 16, K = 128 keys), out_proj,
 //     linear1, linear2.  Attention is computed for all 128 token rows of the CTA at once and the softmax masks the keys of
 //     other boards (block-diagonal), so boards never mix;
-//   * LayerNorm, bias, ReLU, the softmax and the operand re-layouts run on 8 warps (TMEM lane quarter x column half),
-//     each thread owning one token row of its half of the columns; V is written transposed (keys along K) for O = P V;
+//   * LayerNorm, bias, ReLU, the softmax and the operand re-layouts run on 16 warps (TMEM lane quarter x column quarter:
+//     the phases are latency-bound, 8 warps took twice as long),
+//     each thread owning one token row of its part of the columns; V is written transposed (keys along K) for O = P V;
 //   * weights stream through a two-slot ring of 1-D TMA bulk copies in consumption order (at most 36 KB per tile:
 //     in_proj / linear1 split along N, linear2 along K at D = 96), requested two tiles ahead.
 // Shared memory: operand buffer A (LayerNorm output / softmax P / attention output, 32 KB), operand buffer B (Q, K, V^T,
@@ -28,14 +29,16 @@
 namespace tf {
 using namespace mnk_umma;
 constexpr int kRows = 128;
-constexpr int kWorkers = 8;                    // warps 0-7: TMEM lane quarter = warp & 3, column half = warp >> 2
-constexpr int kMmaWarp = kWorkers;             // warp 8: MMA issue + weight TMA
+constexpr int kParts = 4;                      // column parts: each token row is shared by kParts threads
+constexpr int kWorkers = 4 * kParts;           // warps 0-15: TMEM lane quarter = warp & 3, column part = warp >> 2
+constexpr int kMmaWarp = kWorkers;             // warp 16: MMA issue + weight TMA
 constexpr int kThreads = 32 * (kMmaWarp + 1);
 constexpr int kTmemCols = 512;
 constexpr int kXCol = 0;                       // residual stream
 constexpr int kWorkCol = 96;                   // GEMM accumulators (in_proj / scores + attention output / linear1)
 constexpr int kPairBarrier = 1;                // named barrier: the 8 worker warps (row-sum exchanges between column halves)
 constexpr float kLnEps = 1e-5f;
+constexpr int kSC = kRows / kParts;            // score columns per thread in the softmax
 
 template <int D, int NH>
 struct Cfg {
@@ -53,7 +56,10 @@ struct Cfg {
     static constexpr int kLayerWeightBytes = NSPLIT * kTileQkv + kTileO + NSPLIT * kTileF1 + NSPLIT * kTileF2;
     static constexpr int kBufA = 16 * 2048;                // P needs 128 key columns = 16 chunks
     static constexpr int kQK = QP / 8 * 2048;              // Q (and K) operand bytes
-    static constexpr int kBufB = (2 * kQK + NH * 4096 > F / 8 * 2048) ? 2 * kQK + NH * 4096 : F / 8 * 2048;
+    // V^T of one head: [key chunk (16)][16 dims][16 B] with the chunks 272 B apart instead of 256 (LBO is a descriptor field):
+    // the 32 lanes of a warp -- four key chunks -- then scatter their 2-byte elements over distinct banks
+    static constexpr int kVtChunk = 272, kVtHead = 16 * kVtChunk;
+    static constexpr int kBufB = (2 * kQK + NH * kVtHead > F / 8 * 2048) ? 2 * kQK + NH * kVtHead : F / 8 * 2048;
     // per-layer fp32 parameters: ln1 g, b [DP] | in_proj bias [3 QP] | out_proj bias [DP] | ln2 g, b [DP] | b1 [F] | b2 [DP]
     static constexpr int oLn1 = 0, oBqkv = 2 * DP, oBo = oBqkv + 3 * QP, oLn2 = oBo + DP, oB1 = oLn2 + 2 * DP, oB2 = oB1 + F;
     static constexpr int kLayerParams = oB2 + DP;
@@ -72,7 +78,7 @@ struct Smem {
     float emb[3][K::DP];                     // cell_embed weight (channel 0, channel 1), bias
     float head_w[3][K::DP];
     float head_b[4];
-    float part[2][kRows][2];                 // column-half partial sums (two slots)
+    float part[kParts][kRows][3];            // partial sums of the column parts (slots 0, 1; the head outputs use it flat)
     alignas(8) unsigned long long full_bar[2];
     unsigned long long mma_bar;
     unsigned int tmem_base;
@@ -104,10 +110,54 @@ MNK_DEV void tmem_ld8(u32 taddr, u32 (&v)[8]) {
                  :
                  : "memory");
 }
+// N columns (a multiple of 8) of this thread's TMEM lane: all loads in flight, ONE wait.  The empty asm statements pin every
+// use of v[] behind the wait (volatile asm statements keep their order; each one redefines its register).
+template <int N>
+MNK_DEV void tmem_ld_cols(u32 taddr, u32 (&v)[N]) {
+    static_assert(N % 8 == 0, "whole 8-column loads");
+#pragma unroll
+    for (int i = 0; i < N / 8; ++i)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[8 * i]), "=r"(v[8 * i + 1]), "=r"(v[8 * i + 2]), "=r"(v[8 * i + 3]), "=r"(v[8 * i + 4]),
+                       "=r"(v[8 * i + 5]), "=r"(v[8 * i + 6]), "=r"(v[8 * i + 7])
+                     : "r"(taddr + (u32)(8 * i)));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("" : "+r"(v[i]));
+}
+// f(c0, v8) for every 8-column chunk of W columns starting at taddr, 32 columns per load batch
+template <int W, class F>
+MNK_DEV void for_cols(u32 taddr, F&& f) {
+    constexpr int B32 = W / 32, R = W % 32;
+    static_assert(R % 8 == 0, "32-column batches and a tail of whole 8-column chunks");
+#pragma unroll 1
+    for (int b = 0; b < B32; ++b) {
+        u32 v[32];
+        tmem_ld_cols<32>(taddr + (u32)(32 * b), v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) f(32 * b + 8 * c, &v[8 * c]);
+    }
+    if constexpr (R != 0) {
+        u32 v[R];
+        tmem_ld_cols<R>(taddr + (u32)(32 * B32), v);
+#pragma unroll
+        for (int c = 0; c < R / 8; ++c) f(32 * B32 + 8 * c, &v[8 * c]);
+    }
+}
 MNK_DEV void tmem_st8(u32 taddr, const u32 (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
                  "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
+}
+MNK_DEV void tmem_st8p(u32 taddr, const u32* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+MNK_DEV float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 MNK_DEV void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 MNK_DEV void pair_sync() { asm volatile("bar.sync %0, %1;" ::"r"(kPairBarrier), "r"(32 * kWorkers) : "memory"); }
@@ -138,13 +188,17 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
     S& sm = *reinterpret_cast<S*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool worker = warp < kWorkers;
-    const int quarter = warp & 3, half = (warp >> 2) & 1;
+    const int quarter = warp & 3, part = (warp >> 2) & (kParts - 1);
     const int row = quarter * 32 + lane;                  // token row = TMEM lane (workers)
     const int T = p.tokens;
     const long long env0 = (long long)blockIdx.x * p.spc;
     const int boards_here = (int)min((long long)p.spc, p.num_envs - env0);
     const int my_board = row / T, my_token = row - my_board * T;
     const bool row_valid = worker && my_board < boards_here;
+    const bool warp_live = worker && quarter * 32 < boards_here * T;       // at least one real token row in this warp
+    // keys of the boards that have a row in this warp (warp-uniform): the softmax skips the 8-column chunks outside
+    const int u_lo = (quarter * 32 / T) * T, u_hi = min((quarter * 32 + 31) / T + 1, boards_here) * T;
+    const bool one_board = u_hi - u_lo == T;                               // all real rows of the warp belong to one board
     const int total_tiles = p.layers * K::kTilesPerLayer;
 
     if (tid == 0) {
@@ -169,6 +223,14 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
     const u32 t_row = tmem + ((u32)(quarter * 32) << 16);     // this thread's TMEM lane
     bool ok = true;
     u32 mma_phase = 0;
+#ifdef TF_TIMELINE   // debug build only (tools/timeline_tf.py): cycle stamps of one mid-grid CTA into error[1..]
+    const long long t_origin = clock64();
+    int stamp_idx = 0;
+    const bool stamper = p.error != nullptr && blockIdx.x == gridDim.x / 2 && tid == 0;
+#define TF_STAMP() do { if (stamper && stamp_idx < 120) p.error[1 + stamp_idx] = (int)(clock64() - t_origin); ++stamp_idx; } while (0)
+#else
+#define TF_STAMP() do { } while (0)
+#endif
 
     // weight tiles in consumption order; tile i sits in ring slot i & 1
     auto tile_bytes = [&](int j) -> u32 {       // j = index within the layer
@@ -211,8 +273,8 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
             (void)c;
         }
 #pragma unroll
-        for (int c8 = 0; c8 < K::DP / 16; ++c8) {
-            const int c0 = half * (K::DP / 2) + 8 * c8;
+        for (int c8 = 0; c8 < K::DP / (8 * kParts); ++c8) {
+            const int c0 = part * (K::DP / kParts) + 8 * c8;
             u32 v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -232,30 +294,37 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
     unsigned char* const hbuf = &sm.bufB[0];
     const float scale = rsqrtf((float)K::DH);
 
-    // LayerNorm of this thread's row (its column half) -> bufA as the next GEMM's A operand
+    // LayerNorm of this thread's row (its column part) -> bufA as the next GEMM's A operand
     auto layer_norm = [&](const float* g, const float* b) {
-        float x[K::DP / 2];
+        float x[K::DP / kParts];
         float sum = 0.f, sq = 0.f;
+        {
+            u32 v[K::DP / kParts];
+            tmem_ld_cols<K::DP / kParts>(t_row + (u32)(kXCol + part * (K::DP / kParts)), v);
+            float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};     // four independent chains
 #pragma unroll
-        for (int c8 = 0; c8 < K::DP / 16; ++c8) {
-            u32 v[8];
-            tmem_ld8(t_row + (u32)(kXCol + half * (K::DP / 2) + 8 * c8), v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                x[8 * c8 + j] = __uint_as_float(v[j]);
-                sum += x[8 * c8 + j];
-                sq = fmaf(x[8 * c8 + j], x[8 * c8 + j], sq);
+            for (int j = 0; j < K::DP / kParts; ++j) {
+                x[j] = __uint_as_float(v[j]);
+                s4[j & 3] += x[j];
+                q4[j & 3] = fmaf(x[j], x[j], q4[j & 3]);
             }
+            sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
         }
-        sm.part[half][row][0] = sum;
-        sm.part[half][row][1] = sq;
+        sm.part[part][row][0] = sum;
+        sm.part[part][row][1] = sq;
         pair_sync();
-        const float tot = sm.part[0][row][0] + sm.part[1][row][0], tsq = sm.part[0][row][1] + sm.part[1][row][1];
+        float tot = 0.f, tsq = 0.f;
+#pragma unroll
+        for (int q = 0; q < kParts; ++q) {
+            tot += sm.part[q][row][0];
+            tsq += sm.part[q][row][1];
+        }
         const float mean = tot * (1.0f / D);
         const float rstd = rsqrtf(fmaxf(tsq * (1.0f / D) - mean * mean, 0.f) + kLnEps);
 #pragma unroll
-        for (int c8 = 0; c8 < K::DP / 16; ++c8) {
-            const int c0 = half * (K::DP / 2) + 8 * c8;
+        for (int c8 = 0; c8 < K::DP / (8 * kParts); ++c8) {
+            const int c0 = part * (K::DP / kParts) + 8 * c8;
             u32 w[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -266,17 +335,15 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
             *reinterpret_cast<uint4*>(bufA + ((size_t)(c0 / 8) * kRows + row) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
         }
     };
-    // x[row][half columns] += bias (the bias of a GEMM that accumulates into the residual stream)
+    // x[row][this thread's columns] += bias (the bias of a GEMM that accumulates into the residual stream)
     auto add_bias_to_x = [&](const float* bias) {
+        const int c0 = part * (K::DP / kParts);
+        u32 v[K::DP / kParts];
+        tmem_ld_cols<K::DP / kParts>(t_row + (u32)(kXCol + c0), v);
 #pragma unroll
-        for (int c8 = 0; c8 < K::DP / 16; ++c8) {
-            const int c0 = half * (K::DP / 2) + 8 * c8;
-            u32 v[8];
-            tmem_ld8(t_row + (u32)(kXCol + c0), v);
+        for (int j = 0; j < K::DP / kParts; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + bias[c0 + j]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + bias[c0 + j]);
-            tmem_st8(t_row + (u32)(kXCol + c0), v);
-        }
+        for (int c8 = 0; c8 < K::DP / (8 * kParts); ++c8) tmem_st8p(t_row + (u32)(kXCol + c0 + 8 * c8), &v[8 * c8]);
         tmem_st_wait();
     };
     // all threads: wait for the commit of the MMAs just issued
@@ -298,6 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
         __syncthreads();
         if (worker) layer_norm(&sm.prm[K::oLn1], &sm.prm[K::oLn1 + K::DP]);
         phase_sync();
+        TF_STAMP();
         // ---- in_proj: [Q | K | V] = LN1(x) Wqkv^T ------------------------------------------------------------------------
         if (warp == kMmaWarp) {
             for (int j = 0; j < K::NSPLIT; ++j) {
@@ -310,17 +378,15 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
             __syncwarp();
         }
         wait_mma();
+        TF_STAMP();
         if (warp == kMmaWarp && elect_one())
             for (int j = 0; j < K::NSPLIT; ++j) request_tile(tile + j + 2);
         tile += K::NSPLIT;
         // ---- + bias, Q scaled, operands for the attention: Q, K as [chunk][token][16 B], V transposed ------------------
         if (worker) {
-            constexpr int W = 3 * K::QP / 2;     // columns per half
-#pragma unroll 1
-            for (int c8 = 0; c8 < W / 8; ++c8) {
-                const int c0 = half * W + 8 * c8;
-                u32 v[8];
-                tmem_ld8(t_row + (u32)(kWorkCol + c0), v);
+            constexpr int W = 3 * K::QP / kParts;     // columns per part
+            for_cols<W>(t_row + (u32)(kWorkCol + part * W), [&](int rel, const u32* v) {
+                const int c0 = part * W + rel;
                 float y[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) y[j] = __uint_as_float(v[j]) + sm.prm[K::oBqkv + c0 + j];
@@ -334,17 +400,21 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
                     *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
                 } else {
                     const int head = within / 16, d0 = within & 15;
-                    unsigned char* dst = vtbuf + (size_t)head * 4096 + ((size_t)(row >> 3) * 16 + d0) * 16 + (row & 7) * 2;
+                    unsigned char* dst = vtbuf + (size_t)head * K::kVtHead + (size_t)(row >> 3) * K::kVtChunk + d0 * 16 + (row & 7) * 2;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<unsigned short*>(dst + j * 16) = (unsigned short)(act_pack2(y[j], 0.f) & 0xFFFFu);
                 }
-            }
+            });
         }
         phase_sync();
+        TF_STAMP();
         // ---- attention, head by head: S = Q K^T -> softmax over this board's keys -> O = P V -------------------------------
+#ifndef TF_EXP_HEADS          // timing experiments only (wrong results): how many heads run
+#define TF_EXP_HEADS NH
+#endif
 #pragma unroll 1
-        for (int h = 0; h < NH; ++h) {
+        for (int h = 0; h < TF_EXP_HEADS; ++h) {
             if (warp == kMmaWarp) {
                 if (elect_one()) {
                     issue_gemm(tmem + (u32)kWorkCol, smem_u32(qbuf) + (u32)(h * 2 * 2048), 1, smem_u32(kbuf) + (u32)(h * 2 * 2048), 128, false);
@@ -353,50 +423,117 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
                 __syncwarp();
             }
             wait_mma();
-            if (worker) {
-                float e[64];
-                float mx = -INFINITY;
-                const int lo = my_board * T, hi = row_valid ? lo + T : lo;       // this board's keys
+            TF_STAMP();
+        TF_STAMP();
+#ifdef TF_EXP_NO_SOFTMAX
+            if (false) {
+#else
+            if (worker && !warp_live) {
+#endif
+                // every row of this warp is padding: P = 0 for them, no arithmetic (the exchanges still take place)
+#ifndef TF_EXP_NO_PAIRSYNC
+                pair_sync();
+                pair_sync();
+#endif
 #pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    u32 v[8];
-                    tmem_ld8(t_row + (u32)(kWorkCol + 64 * half + 8 * c8), v);
+                for (int c8 = 0; c8 < kSC / 8; ++c8)
+                    *reinterpret_cast<uint4*>(bufA + ((size_t)(kSC / 8 * part + c8) * kRows + row) * 16) = make_uint4(0, 0, 0, 0);
+#ifdef TF_EXP_NO_SOFTMAX
+            } else if (false) {
+#else
+            } else if (worker) {
+#endif
+                float e[kSC];
+                // this board's keys; a padding row of a single-board warp keeps that board's keys (its result is never used,
+                // it only has to stay finite)
+                const int lo = one_board ? u_lo : my_board * T, hi = one_board ? u_hi : (row_valid ? lo + T : lo);
+                float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // four independent chains
+                {
+                    u32 v[kSC];
+                    tmem_ld_cols<kSC>(t_row + (u32)(kWorkCol + kSC * part), v);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int col = 64 * half + 8 * c8 + j;
-                        e[8 * c8 + j] = (col >= lo && col < hi) ? __uint_as_float(v[j]) : -INFINITY;
-                        mx = fmaxf(mx, e[8 * c8 + j]);
+                    for (int c8 = 0; c8 < kSC / 8; ++c8) {
+                        // keys of no board that has a row in this warp: nothing to compute (warp-uniform branch) -- at 9x9 a
+                        // CTA holds one board, 47 of its 128 key columns and 47 of its rows are padding
+                        const int col0 = kSC * part + 8 * c8;
+                        if (one_board && col0 >= u_lo && col0 + 8 <= u_hi) {
+                            // every row of the warp sees all 8 keys (its padding rows may see anything finite): no masks
+#pragma unroll
+                            for (int j = 8 * c8; j < 8 * c8 + 8; ++j) {
+                                e[j] = __uint_as_float(v[j]);
+                                m4[j & 3] = fmaxf(m4[j & 3], e[j]);
+                            }
+                        } else if (col0 + 8 > u_lo && col0 < u_hi) {
+#pragma unroll
+                            for (int j = 8 * c8; j < 8 * c8 + 8; ++j) {
+                                const int col = kSC * part + j;
+                                e[j] = (col >= lo && col < hi) ? __uint_as_float(v[j]) : -INFINITY;
+                                m4[j & 3] = fmaxf(m4[j & 3], e[j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 8 * c8; j < 8 * c8 + 8; ++j) e[j] = -INFINITY;
+                        }
                     }
                 }
-                sm.part[half][row][0] = mx;
+                float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+                sm.part[part][row][0] = mx;
+#ifndef TF_EXP_NO_PAIRSYNC
                 pair_sync();
-                mx = fmaxf(sm.part[0][row][0], sm.part[1][row][0]);
-                float sum = 0.f;
+#endif
+                mx = fmaxf(fmaxf(sm.part[0][row][0], sm.part[1][row][0]), fmaxf(sm.part[2][row][0], sm.part[3][row][0]));
+                if (mx == -INFINITY) mx = 0.f;                                   // a padding row with no key at all: P = 0, not NaN
+                const float mxl = mx * 1.4426950408889634f;                      // exp(s - mx) = exp2(s * log2(e) - mx * log2(e))
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                    e[j] = (e[j] == -INFINITY) ? 0.f : __expf(e[j] - mx);
-                    sum += e[j];
+                for (int c8 = 0; c8 < kSC / 8; ++c8) {
+                    const int col0 = kSC * part + 8 * c8;
+                    if (col0 + 8 > u_lo && col0 < u_hi) {
+#pragma unroll
+                        for (int j = 8 * c8; j < 8 * c8 + 8; ++j) {
+#ifdef TF_EXP_NO_EXP
+                            e[j] = (e[j] == -INFINITY) ? 0.f : fmaf(e[j], 1.4426950408889634f, -mxl);
+#else
+                            e[j] = fast_exp2(fmaf(e[j], 1.4426950408889634f, -mxl));      // ex2.approx(-inf) = +0: masked keys vanish
+#endif
+                            s4[j & 3] += e[j];
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 8 * c8; j < 8 * c8 + 8; ++j) e[j] = 0.f;
+                    }
                 }
-                sm.part[half][row][1] = sum;
+                float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                sm.part[part][row][1] = sum;
+#ifndef TF_EXP_NO_PAIRSYNC
                 pair_sync();
-                sum = sm.part[0][row][1] + sm.part[1][row][1];
-                const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+#endif
+                sum = (sm.part[0][row][1] + sm.part[1][row][1]) + (sm.part[2][row][1] + sm.part[3][row][1]);
+                const float inv = sum > 0.f ? __frcp_rn(sum) : 0.f;
 #pragma unroll
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    u32 w[4];
+                for (int c8 = 0; c8 < kSC / 8; ++c8) {
+                    u32 w[4] = {0u, 0u, 0u, 0u};
+                    const int col0 = kSC * part + 8 * c8;
+                    if (col0 + 8 > u_lo && col0 < u_hi) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) w[q] = act_pack2(e[8 * c8 + 2 * q] * inv, e[8 * c8 + 2 * q + 1] * inv);
-                    *reinterpret_cast<uint4*>(bufA + ((size_t)(8 * half + c8) * kRows + row) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                        for (int q = 0; q < 4; ++q) w[q] = act_pack2(e[8 * c8 + 2 * q] * inv, e[8 * c8 + 2 * q + 1] * inv);
+                    }
+                    *reinterpret_cast<uint4*>(bufA + ((size_t)(kSC / 8 * part + c8) * kRows + row) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
             phase_sync();
+            TF_STAMP();
+        TF_STAMP();
             if (warp == kMmaWarp) {
                 if (elect_one()) {
                     // O_h[128 x 16] = P[128 x 128 keys] V_h: B = V^T_h as [key chunk][16 dims][16 B]
                     const u32 idesc = umma_idesc_bf16(16);
-                    for (int ks = 0; ks < 8; ++ks) {
+#ifndef TF_EXP_PV_KSTEPS
+#define TF_EXP_PV_KSTEPS 8
+#endif
+                    for (int ks = 0; ks < TF_EXP_PV_KSTEPS; ++ks) {
                         const u64 a_d = umma_desc(smem_u32(bufA) + (u32)(ks * 2 * 2048), 2048, 128);
-                        const u64 b_d = umma_desc(smem_u32(vtbuf) + (u32)(h * 4096 + ks * 2 * 256), 256, 128);
+                        const u64 b_d = umma_desc(smem_u32(vtbuf) + (u32)(h * K::kVtHead + ks * 2 * K::kVtChunk), K::kVtChunk, 128);
                         umma_bf16(tmem + (u32)(kWorkCol + 128 + 16 * h), a_d, b_d, idesc, ks != 0);
                     }
                     umma_commit(&sm.mma_bar);
@@ -404,22 +541,21 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
                 __syncwarp();
             }
             wait_mma();            // P (bufA) and the score columns are free again
+            TF_STAMP();
         }
         // ---- attention output -> bufA as the out_proj operand; x += out_proj bias ------------------------------------------
         if (worker) {
-#pragma unroll 1
-            for (int c8 = 0; c8 < K::QP / 16; ++c8) {
-                const int c0 = half * (K::QP / 2) + 8 * c8;
-                u32 v[8];
-                tmem_ld8(t_row + (u32)(kWorkCol + 128 + c0), v);
+            for_cols<K::QP / kParts>(t_row + (u32)(kWorkCol + 128 + part * (K::QP / kParts)), [&](int rel, const u32* v) {
+                const int c0 = part * (K::QP / kParts) + rel;
                 u32 w[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) w[q] = act_pack2(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
                 *reinterpret_cast<uint4*>(bufA + ((size_t)(c0 / 8) * kRows + row) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+            });
             add_bias_to_x(&sm.prm[K::oBo]);
         }
         phase_sync();
+        TF_STAMP();
         // ---- out_proj, accumulated into the residual stream --------------------------------------------------------------------
         if (warp == kMmaWarp) {
             wait_tile(tile);
@@ -430,11 +566,13 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
             __syncwarp();
         }
         wait_mma();
+        TF_STAMP();
         if (warp == kMmaWarp && elect_one()) request_tile(tile + 2);
         tile += 1;
         // ---- LayerNorm2 -> bufA; linear1 ------------------------------------------------------------------------------------------
         if (worker) layer_norm(&sm.prm[K::oLn2], &sm.prm[K::oLn2 + K::DP]);
         phase_sync();
+        TF_STAMP();
         if (warp == kMmaWarp) {
             for (int j = 0; j < K::NSPLIT; ++j) {
                 wait_tile(tile + j);
@@ -446,27 +584,26 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
             __syncwarp();
         }
         wait_mma();
+        TF_STAMP();
         if (warp == kMmaWarp && elect_one())
             for (int j = 0; j < K::NSPLIT; ++j) request_tile(tile + j + 2);
         tile += K::NSPLIT;
         // ---- + bias, ReLU -> hidden activations (bufB) as the linear2 operand; x += linear2 bias -----------------------------
         if (worker) {
-            constexpr int W = K::F / 2;
-#pragma unroll 1
-            for (int c8 = 0; c8 < W / 8; ++c8) {
-                const int c0 = half * W + 8 * c8;
-                u32 v[8];
-                tmem_ld8(t_row + (u32)(kWorkCol + c0), v);
+            constexpr int W = K::F / kParts;
+            for_cols<W>(t_row + (u32)(kWorkCol + part * W), [&](int rel, const u32* v) {
+                const int c0 = part * W + rel;
                 u32 w[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     w[q] = act_pack2(fmaxf(__uint_as_float(v[2 * q]) + sm.prm[K::oB1 + c0 + 2 * q], 0.f),
                                      fmaxf(__uint_as_float(v[2 * q + 1]) + sm.prm[K::oB1 + c0 + 2 * q + 1], 0.f));
                 *reinterpret_cast<uint4*>(hbuf + ((size_t)(c0 / 8) * kRows + row) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+            });
             add_bias_to_x(&sm.prm[K::oB2]);
         }
         phase_sync();
+        TF_STAMP();
         // ---- linear2, accumulated into the residual stream ----------------------------------------------------------------------
         if (warp == kMmaWarp) {
             for (int j = 0; j < K::NSPLIT; ++j) {
@@ -479,6 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
             __syncwarp();
         }
         wait_mma();
+        TF_STAMP();
         if (warp == kMmaWarp && elect_one())
             for (int j = 0; j < K::NSPLIT; ++j) request_tile(tile + j + 2);
         tile += K::NSPLIT;
@@ -487,13 +625,12 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
     // ---- the 1x1 convolutions that open the two heads (Conv1d(D, 2, 1), Conv1d(D, 1, 1)) -------------------------------------
     if (worker) {
         float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+        {
+            const int c0 = part * (K::DP / kParts);
+            u32 v[K::DP / kParts];
+            tmem_ld_cols<K::DP / kParts>(t_row + (u32)(kXCol + c0), v);
 #pragma unroll
-        for (int c8 = 0; c8 < K::DP / 16; ++c8) {
-            const int c0 = half * (K::DP / 2) + 8 * c8;
-            u32 v[8];
-            tmem_ld8(t_row + (u32)(kXCol + c0), v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < K::DP / kParts; ++j) {
                 const float x = __uint_as_float(v[j]);
                 h0 = fmaf(x, sm.head_w[0][c0 + j], h0);
                 h1 = fmaf(x, sm.head_w[1][c0 + j], h1);
@@ -501,14 +638,24 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
             }
         }
         pair_sync();                            // the softmax / LayerNorm readers of `part` are done
-        float* mine = &sm.part[0][0][0] + 3 * row;     // `part` as a flat array: three floats per row
-        if (half == 1) { mine[0] = h0; mine[1] = h1; mine[2] = h2; }
+        float* flat = &sm.part[0][0][0];        // `part` as a flat array: [3 outputs][kParts - 1 parts][128 rows] = 1,152 of its 1,536 floats
+        if (part != 0) {
+            flat[(0 * (kParts - 1) + part - 1) * kRows + row] = h0;
+            flat[(1 * (kParts - 1) + part - 1) * kRows + row] = h1;
+            flat[(2 * (kParts - 1) + part - 1) * kRows + row] = h2;
+        }
         pair_sync();
-        if (half == 0 && row_valid) {
+        if (part == 0 && row_valid) {
+#pragma unroll
+            for (int q = 0; q < kParts - 1; ++q) {
+                h0 += flat[(0 * (kParts - 1) + q) * kRows + row];
+                h1 += flat[(1 * (kParts - 1) + q) * kRows + row];
+                h2 += flat[(2 * (kParts - 1) + q) * kRows + row];
+            }
             const long long e = env0 + my_board;
-            p.policy_feat[(size_t)e * 2 * T + my_token] = h0 + mine[0] + sm.head_b[0];
-            p.policy_feat[(size_t)e * 2 * T + T + my_token] = h1 + mine[1] + sm.head_b[1];
-            p.value_feat[(size_t)e * T + my_token] = h2 + mine[2] + sm.head_b[2];
+            p.policy_feat[(size_t)e * 2 * T + my_token] = h0 + sm.head_b[0];
+            p.policy_feat[(size_t)e * 2 * T + T + my_token] = h1 + sm.head_b[1];
+            p.value_feat[(size_t)e * T + my_token] = h2 + sm.head_b[2];
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -8,8 +8,9 @@ The reference writes ``<dir>/model_00042.pt`` (a plain ``state_dict``) next to `
 ``torch.compile``-wrapped module (``_orig_mod.`` prefix, model_export.py:167-174) are accepted.
 
 The convolutional families are constructed here (``mnk_b200.nets.ARCHITECTURES``: resnet_b_s -- the network of the
-accelerated path -- resnet_b_l, cnn_b_s, cnn_b_l and the older resnet_s / resnet_l / cnn_s / cnn_l); the transformer names
-raise, so a caller falls back to the reference's own loader for them rather than silently getting a different network.
+accelerated path -- resnet_b_l, cnn_b_s, cnn_b_l, transformer_b_s, transformer_b_l and the older resnet_s / resnet_l / cnn_s /
+cnn_l); other names (transformer_s / _l, the sgrtransformer transformer_c_*) raise, so a caller falls back to the reference's
+own loader for them rather than silently getting a different network.
 """
 from __future__ import annotations
 

@@ -6,7 +6,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "rl-selfplay-mnk_b200")); sys.path.insert(0, ROOT)
 import torch
-from mnk_b200 import (NativeConvNet, NativeNNPolicy, NativeResNet, build_architecture, RandomPolicy, ResNetActorCritic, RolloutBuffer, RolloutCollector,
+from mnk_b200 import (NativeConvNet, NativeNNPolicy, NativeResNet, build_architecture, native_network, RandomPolicy, ResNetActorCritic, RolloutBuffer, RolloutCollector,
                       TorchSelfPlayWrapper, TorchVectorMnkEnv, masked_sample)
 
 
@@ -87,6 +87,16 @@ def exercise_all():
         wide = NativeConvNet(build_architecture(arch, (2, m, n), m * n).cuda().eval())
         wide.forward_env(env, swap=(torch.arange(ne, device="cuda") % 2).to(torch.uint8))
         wide.check_error()
+    # the transformers: one board per CTA (9x9), several (3x3: 14, 7x7: 2), all 128 token rows (8x16)
+    for arch, (m, n, k, ne) in [("transformer_b_s", (9, 9, 5, 5)), ("transformer_b_s", (3, 3, 3, 31)), ("transformer_b_l", (7, 7, 4, 9)),
+                                ("transformer_b_l", (8, 16, 5, 3))]:
+        env = TorchVectorMnkEnv(m, n, k, ne, device="cuda")
+        env.reset()
+        for t in range(m * n // 3):
+            env.step_autoreset(env.random_legal_actions(8, t), materialise=False)
+        tfm = native_network(build_architecture(arch, (2, m, n), m * n).cuda().eval())
+        tfm.forward_env(env, swap=(torch.arange(ne, device="cuda") % 2).to(torch.uint8))
+        tfm.check_error()
     torch.cuda.synchronize()
 
 

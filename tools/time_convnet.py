@@ -1,20 +1,24 @@
-"""Times mnk_conv_tower (the wider convolutional bodies) alone with CUDA events: useful TFLOP/s against the measured
+"""Times mnk_conv_tower / mnk_transformer_body (the wider convolutional and the transformer bodies) alone with CUDA events:
+useful TFLOP/s (3x3 convolutions; for transformers the Linear / attention matmuls of the reference module) against the measured
 bf16 peak, and the same eval-mode forward through the stock torch module (fp32 / TF32 and bf16 autocast).
    python tools/time_convnet.py [arch] [m n k]"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "rl-selfplay-mnk_b200")); sys.path.insert(0, ROOT)
 import torch
-from mnk_b200 import NativeConvNet, TorchVectorMnkEnv, build_architecture, _lib
+from mnk_b200 import TorchVectorMnkEnv, build_architecture, native_network, _lib
 if os.environ.get("MNK_LIB"):
     _lib.LIB_PATH = os.path.abspath(os.environ["MNK_LIB"])
 arch = sys.argv[1] if len(sys.argv) > 1 else "resnet_b_l"
 m, n, k = (int(x) for x in (sys.argv[2:5] if len(sys.argv) > 4 else (9, 9, 5)))
 torch.manual_seed(0)
 net = build_architecture(arch, (2, m, n), m * n).cuda().eval()
-native = NativeConvNet(net)
+native = native_network(net)
 convs = [mod for mod in net.modules() if isinstance(mod, torch.nn.Conv2d) and mod.kernel_size == (3, 3)]
 flops = sum(2 * m * n * c.in_channels * c.out_channels * 9 for c in convs)
+if hasattr(net, "transformer"):      # per layer: in_proj + out_proj + feed-forward (12 D^2 MACs per token) + QK^T and PV (2 T D per token)
+    D, T = net.embed_dim, m * n
+    flops = net.num_layers * (2 * T * 12 * D * D + 2 * 2 * T * T * D)
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops_sustained": 1391.8}
 for ne in (4096, 32768)[: int(os.environ.get("MNK_SIZES", 2))]:
     env = TorchVectorMnkEnv(m, n, k, ne, device="cuda")
