@@ -64,14 +64,19 @@ class PPOAgent:
                                           process_group=process_group, world_size=world_size)
         if world_size > 1:          # replicas start from rank 0's parameters / buffers / optimiser state
             broadcast_module(self.network, self.optimizer, group=process_group)
-        # Rollout forward on the tcgen05 path with TRAIN-mode BatchNorm -- the reference's rollout never leaves train
-        # mode (src/alg/ppo.py:97) -- for the accelerated architecture (resnet_b_s layout, boards up to 10 rows); any
-        # other module keeps the generic path (stock PyTorch forward on f32 observations).
+        # Rollout forward on the tcgen05 path with the semantics of the reference's rollout, which never leaves train mode
+        # (src/alg/ppo.py:97): TRAIN-mode BatchNorm for the default architecture (resnet_b_s layout, boards up to 10 rows);
+        # the transformers have neither BatchNorm nor dropout, so their native forward is already exact.  Any other module
+        # keeps the generic path (stock PyTorch forward on f32 observations).
         self.native, self.graph_rollout = None, graph_rollout
-        if native_rollout and obs_shape[1] <= 10:
+        if native_rollout:
+            from . import transformer
             from .resnet import NativeResNet
             try:
-                self.native = NativeResNet(self.network, device=self.device, bn_mode="train")
+                if transformer.supports(self.network):
+                    self.native = transformer.NativeTransformer(self.network, device=self.device)
+                elif obs_shape[1] <= 10:
+                    self.native = NativeResNet(self.network, device=self.device, bn_mode="train")
             except (ValueError, AttributeError):
                 self.native = None
 
@@ -81,7 +86,8 @@ class PPOAgent:
         if native:
             stats = self.collector.collect(self.native, vec_env, self.buffer, graph=self.graph_rollout)       # :93-124
             _, last_values = self.native.forward_env(vec_env.env, swap=vec_env._side)    # :131-135 (train mode there too)
-            self.native.export_running_stats(self.network)      # the update continues from the rollout's statistics
+            if hasattr(self.native, "export_running_stats"):
+                self.native.export_running_stats(self.network)  # the update continues from the rollout's statistics
         else:
             stats = self.collector.collect(self.network, vec_env, self.buffer)
             obs = self.collector._last_obs

@@ -137,3 +137,36 @@ def test_update_networks_matches_the_reference_update(autocast, epochs, batch):
     print(f"  |drop-in - reference| / |reference - initial| over all parameters and buffers = {drift:.2e} "
           f"(two runs of the reference itself: {self_drift:.2e})")
     assert drift <= (1e-5 if one else 2e-2 if autocast is None else 0.1)
+
+
+def test_transformer_agent_rolls_out_on_the_native_forward():
+    """PPOAgent with a transformer_b_s agent collects its rollout on mnk_transformer_body (no BatchNorm / dropout: the native
+    forward IS the train-mode forward): the stored log-probs and values agree with the torch module evaluated on the stored
+    observations and actions, the update runs, and the refreshed native weights follow the optimiser step."""
+    from mnk_b200 import NativeTransformer, PPOAgent, RandomPolicy, TorchSelfPlayWrapper, TorchVectorMnkEnv, build_architecture
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ne, steps = 256, 8
+    env = TorchVectorMnkEnv(3, 3, 3, ne, device=DEV)
+    wr = TorchSelfPlayWrapper(env, seed=1)
+    wr.set_opponent(RandomPolicy(9, seed=3))
+    net = build_architecture("transformer_b_s", (2, 3, 3), 9).to(DEV)
+    with torch.no_grad():
+        net.policy_head[7].weight.mul_(30.0)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    agent = PPOAgent((2, 3, 3), 9, net, n_steps=steps, optimizer=opt, batch_size=512, ppo_epochs=2, num_envs=ne, device=DEV, k=3)
+    assert isinstance(agent.native, NativeTransformer)
+    stats = agent.collector.collect(agent.native, wr, agent.buffer)
+    agent.native.check_error()
+    buf = agent.buffer
+    obs, mask = buf.gather_obs(None, steps * ne)
+    with torch.no_grad():
+        dist, value = net.train()(obs, mask)
+        want_lp = dist.log_prob(buf.actions[:steps].reshape(-1))
+    assert float((want_lp - buf.log_probs[:steps].reshape(-1)).abs().max()) <= 3e-3
+    assert float((value.reshape(-1) - buf.values[:steps].reshape(-1)).abs().max()) <= 1e-2      # (LayerNorm over 9 features)
+    version = agent.native.version
+    buf.reset()
+    m = agent.learn(wr)
+    assert np.isfinite(m.actor_loss) and np.isfinite(m.critic_loss) and m.fps > 0
+    assert agent.native.version == version + 1 and stats.agent_steps == steps * ne
