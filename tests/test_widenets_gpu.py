@@ -175,3 +175,22 @@ def test_transformer_unsupported_shapes_raise():
         NativeTransformer(TransformerActorCritic((2, 9, 9), 81, embed_dim=64, num_layers=2, num_heads=4).to(DEV))
     with pytest.raises(ValueError):
         NativeTransformer(build_architecture("transformer_b_s", (2, 13, 13), 169).to(DEV))      # 169 tokens > 128
+
+
+@pytest.mark.parametrize("arch", ["resnet_b_l", "cnn_b_s", "transformer_b_s", "transformer_b_l"])
+def test_native_forwards_are_deterministic(arch):
+    """Back-to-back launches on the same state agree bit for bit (no atomics, fixed reduction orders) -- also a cheap race
+    detector for the hand-rolled pipelines (weight rings, phase barriers)."""
+    from mnk_b200 import TorchVectorMnkEnv, build_architecture, native_network
+    torch.manual_seed(1)
+    m, n, k, ne = 9, 9, 5, 3000
+    native = native_network(build_architecture(arch, (2, m, n), m * n).to(DEV).eval(), device=DEV)
+    env = TorchVectorMnkEnv(m, n, k, ne, device=DEV)
+    env.reset()
+    for t in range(30):
+        env.step_autoreset(env.random_legal_actions(2, t), materialise=False)
+    first = native.features(env._st, ne, m * n, None)
+    for _ in range(20):
+        again = native.features(env._st, ne, m * n, None)
+        assert torch.equal(again[0], first[0]) and torch.equal(again[1], first[1])
+    native.check_error()
