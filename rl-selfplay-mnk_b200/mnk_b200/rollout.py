@@ -235,7 +235,7 @@ class RolloutCollector:
                 if state is not None:                      # a train-mode BatchNorm forward: it must not count
                     network.restore_running_state(state)
                 opp = vec_env.opponent_policy
-                if hasattr(opp, "net"):
+                if getattr(opp, "net", None) is not None:
                     opp.net.forward_env(vec_env.env)
             self._graph_base = torch.zeros(1, dtype=torch.int64, device=self._dev)
             self._graph_totals = torch.zeros(6, dtype=torch.float64, device=self._dev)

@@ -133,7 +133,8 @@ class TorchSelfPlayWrapper:
             else:
                 if opp is None:
                     raise RuntimeError("TorchSelfPlayWrapper: set_opponent() has not been called")
-                from_bits = hasattr(opp, "act_from_env")     # native policies read the bitboards: no f32 opponent view
+                # native policies read the bitboards: no f32 opponent view
+                from_bits = callable(getattr(opp, "act_from_env", None)) and getattr(opp, "reads_bitboards", True)
                 opp_obs, opp_mask = (None, None) if from_bits else env._new_obs()
                 check(self._L.mnk_selfplay_agent(env._stp, self._spp, _ptr(a), _ptr(forced), _ptr(rewards),
                                                   _ptr(terminated), _ptr(self._opp_active), _ptr(opp_obs), _ptr(opp_mask),

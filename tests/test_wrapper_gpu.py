@@ -354,3 +354,41 @@ def test_agent_side_is_a_live_writable_mirror():
     assert torch.equal(obs["observation"], raw["observation"].flip(1))       # canonical view now swaps the planes
     wr.reset(options={"agent_side": torch.arange(64, device=DEV) % 2})
     assert torch.equal(side, torch.arange(64, device=DEV) % 2)               # the held tensor follows
+
+
+def test_dropin_nnpolicy_runs_supported_models_on_the_native_forward():
+    """selfplay.policy.NNPolicy -- the class the reference's train.py constructs for every opponent -- picks the tcgen05
+    forward for the architectures that have one: same legal moves, logits-level agreement with the torch forward, weights
+    re-imported after an in-place update, `native=False` keeps the torch path."""
+    from selfplay.policy import NNPolicy
+    from mnk_b200 import NativeConvNet, NativeResNet, NativeTransformer, TorchSelfPlayWrapper, TorchVectorMnkEnv, build_architecture
+    torch.manual_seed(4)
+    for arch, cls in (("resnet_b_s", NativeResNet), ("cnn_b_s", NativeConvNet), ("transformer_b_s", NativeTransformer)):
+        model = build_architecture(arch, (2, 9, 9), 81).to(DEV)
+        with torch.no_grad():                    # (0.01-gain initialisation: make the logits non-flat)
+            (model.policy_head if hasattr(model, "policy_head") else model.actor)[7].weight.mul_(60.0)
+        pol = NNPolicy(model, seed=5)
+        assert isinstance(pol.net, cls) and pol.reads_bitboards and not model.training
+        torch_pol = NNPolicy(model, seed=5, native=False)
+        assert torch_pol.net is None and not torch_pol.reads_bitboards
+        env = TorchVectorMnkEnv(9, 9, 5, 300, device=DEV, strict=True)
+        wr = TorchSelfPlayWrapper(env, seed=2)
+        wr.set_opponent(pol)
+        obs, _ = wr.reset()
+        for t in range(12):
+            obs, r, term, _, _ = wr.step(torch.multinomial(obs["action_mask"].float(), 1).squeeze(1))
+        pol.net.check_error()
+        # deterministic actions from f32 observations: native vs torch forward agree wherever the top-2 gap is clear
+        a_native, a_torch = pol.act(obs, deterministic=True), torch_pol.act(obs, deterministic=True)
+        with torch.no_grad():
+            d, _ = model(obs["observation"], obs["action_mask"])
+        top2 = torch.topk(d.logits, 2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-2 * d.logits[torch.isfinite(d.logits)].abs().max()
+        assert bool((a_native == a_torch)[clear].all()) and int(clear.sum()) > 0
+        assert bool(obs["action_mask"].gather(1, a_native[:, None]).all())
+        # an in-place update of the module is picked up
+        before = pol.net.version
+        with torch.no_grad():
+            next(model.parameters()).mul_(1.01)
+        pol.act(obs, deterministic=True)
+        assert pol.net.version == before + 1
