@@ -223,10 +223,13 @@ class RolloutCollector:
         # captured objects (an id() can be recycled once its object dies) plus their pointer signatures: NativeResNet
         # keeps its weight tensors at stable addresses across refresh() and reports any re-allocation through
         # `pointer_signature()`, so a replay can never read freed or stale weight storage.
-        opp = vec_env.opponent_policy
-        sig = tuple(o.pointer_signature() if hasattr(o, "pointer_signature") else None
-                    for o in (network, getattr(opp, "net", None)))
-        key = (network, vec_env, buffer, steps, opp, sig, buffer.packed_obs.data_ptr(), vec_env.env._bits.data_ptr())
+        def make_key():
+            opp_ = vec_env.opponent_policy
+            sig = tuple(o.pointer_signature() if hasattr(o, "pointer_signature") else None
+                        for o in (network, getattr(opp_, "net", None)))
+            return (network, vec_env, buffer, steps, opp_, sig, buffer.packed_obs.data_ptr(), vec_env.env._bits.data_ptr())
+
+        key = make_key()
         old = getattr(self, "_graph_key", None)
         if old is None or len(old) != len(key) or any(a is not b and a != b for a, b in zip(old, key)):
             with torch.no_grad():                          # one-time work that must not happen under capture
@@ -237,6 +240,7 @@ class RolloutCollector:
                 opp = vec_env.opponent_policy
                 if getattr(opp, "net", None) is not None:
                     opp.net.forward_env(vec_env.env)
+            key = make_key()                               # (the warm-up may have allocated the train-mode scratch arrays)
             self._graph_base = torch.zeros(1, dtype=torch.int64, device=self._dev)
             self._graph_totals = torch.zeros(6, dtype=torch.float64, device=self._dev)
             vec_env.counter_base = self._graph_base

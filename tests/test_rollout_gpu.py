@@ -145,3 +145,34 @@ def test_collector_rollout_replays_on_oracle(m, n, k, ne, steps):
     buf.reset()
     col.collect(net, wr, buf)
     assert np.array_equal(buf.observations[0].cpu().numpy(), oobs["observation"])
+
+
+@pytest.mark.parametrize("agent_arch,opp_arch", [("transformer_b_s", "resnet_b_l"), ("resnet_b_s", "transformer_b_s"), ("cnn_b_s", "cnn_b_s")])
+def test_graph_rollout_with_wide_and_transformer_networks(agent_arch, opp_arch):
+    """RolloutCollector.collect(graph=True) -- the whole rollout as one CUDA graph -- with the other native forwards on either
+    side: captures (torch head tails included), replays with fresh draws, every stored action legal, flags clean."""
+    from mnk_b200 import (NativeNNPolicy, RolloutBuffer, RolloutCollector, TorchSelfPlayWrapper, TorchVectorMnkEnv, build_architecture,
+                          native_network, NativeResNet)
+    torch.manual_seed(3)
+    m, n, k, ne, steps = 9, 9, 5, 700, 6
+    a_net = build_architecture(agent_arch, (2, m, n), m * n).to(DEV)
+    agent = NativeResNet(a_net, device=DEV, bn_mode="train") if agent_arch == "resnet_b_s" else native_network(a_net.eval(), device=DEV)
+    opp = NativeNNPolicy(build_architecture(opp_arch, (2, m, n), m * n).to(DEV), seed=4)
+    env = TorchVectorMnkEnv(m, n, k, ne, device=DEV)
+    wr = TorchSelfPlayWrapper(env, seed=9)
+    wr.set_opponent(opp)
+    buf = RolloutBuffer(steps, ne, (2, m, n), m * n, device=DEV, k=k)
+    col = RolloutCollector(ne, device=DEV, seed=2)
+    wr.reset(materialise=False)
+    col._last_obs = {"observation": None, "action_mask": None}
+    seen = []
+    for rep in range(3):
+        buf.reset()
+        stats = col.collect(agent, wr, buf, graph=True)
+        assert stats.agent_steps == steps * ne and buf.ptr == steps
+        masks = buf.action_masks
+        assert bool(masks.gather(2, buf.actions[:steps].unsqueeze(-1)).all())
+        assert bool(torch.isfinite(buf.log_probs[:steps]).all()) and bool(torch.isfinite(buf.values[:steps]).all())
+        seen.append(buf.actions[:steps].clone())
+    assert not torch.equal(seen[0], seen[1]) and col._graph_replays == 3
+    agent.check_error(), opp.net.check_error()
