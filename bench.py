@@ -106,10 +106,9 @@ class Ctx:
             raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU arm)")
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
-        self.numa = None
-        if self.world > 1:
-            from mnk_b200.dist import pin_to_gpu_numa
-            self.numa = pin_to_gpu_numa(self.local_rank)         # host threads next to this GPU's PCIe root
+        from mnk_b200.dist import pin_to_gpu_numa
+        self.numa = pin_to_gpu_numa(self.local_rank)             # host threads (and the pinned buffers they first touch)
+        if self.world > 1:                                       # next to this GPU's PCIe root
             dist.init_process_group("nccl", device_id=self.dev)
 
     def barrier(self):
@@ -506,7 +505,7 @@ def bench_env_workload(ctx: Ctx, wl: Workload, args, primary: bool):
         for t in range(W):
             launch(t, stream)
 
-    def e2e_loop(slab, reps, host_obs=None, host_mask=None, steps=e2e_steps):
+    def e2e_loop(slab, reps, host_obs=None, host_mask=None, steps=e2e_steps, host_actions=host_actions):
         """K steps per C call (mnk_step_host_loop); wall clock AND device events, the larger counts."""
         out = []
         for _ in range(reps):
@@ -538,7 +537,7 @@ def bench_env_workload(ctx: Ctx, wl: Workload, args, primary: bool):
         return ctx.reduce([max(ev0.elapsed_time(ev1), wall)], "max")[0], good
 
     e2e_reps = 5 if primary else 3
-    slabs = sorted({s for s in (args.e2e_slab, 2, 4, 8) if s <= max(e2e_steps, 1)}) if primary else [args.e2e_slab]
+    slabs = sorted({s for s in (args.e2e_slab, 2, 4, 8, 16) if s <= max(e2e_steps, 1)}) if primary else [args.e2e_slab]
     loop_ms = {}
     for s_ in slabs:
         per, ok_l, (r_h, d_h) = e2e_loop(s_, e2e_reps)
@@ -560,6 +559,10 @@ def bench_env_workload(ctx: Ctx, wl: Workload, args, primary: bool):
         host_mask = torch.empty((full_steps, envs, wl.cells), dtype=torch.bool).pin_memory()
         per, _, _ = e2e_loop(max(1, min(4, ring // 2)), 2, host_obs, host_mask, steps=full_steps)
         full_ms = min(per)
+        host_actions32 = host_actions.to(torch.int32).pin_memory()       # the reference accepts int32 actions too
+        per, ok32, _ = e2e_loop(best_slab, e2e_reps, host_actions=host_actions32)
+        i32_ms = statistics.median(per)
+        verified = verified and ok32
     clocks = sampler.stop()
 
     st = ctx.reduce(stats.tolist(), "sum")          # end-of-run statistics over NCCL
@@ -596,7 +599,8 @@ def bench_env_workload(ctx: Ctx, wl: Workload, args, primary: bool):
         "e2e": {"value": total_envs * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * envs,
                 "d2h_bytes_per_step": 5 * envs, "steps": e2e_steps, "slab_steps": best_slab,
                 "api": "TorchVectorMnkEnv.step_host_loop -> mnk_step_host_loop: all K steps in one C call, pinned int64 actions in, f32 rewards "
-                       "+ bool dones out (bytes are per GPU per step), copies pipelined per slab on side streams, one host wait per slab; "
+                       "+ bool dones out (bytes are per GPU per step), copies pipelined per slab on side streams (copy-in a slab ahead), one "
+                       "kernel launch (mnk_step_slab) and one host wait per slab; "
                        "observation + mask are materialised every step and stay on the device (their consumer is the GPU network) -- see "
                        "full_d2h for a host consumer",
                 "by_slab_steps": {str(s_): total_envs * e2e_steps / (v * 1e-3) for s_, v in loop_ms.items()}},
@@ -611,6 +615,11 @@ def bench_env_workload(ctx: Ctx, wl: Workload, args, primary: bool):
             "note": "TorchVectorMnkEnv.step_host -> mnk_step_host: ONE step per call, stream synchronised every step",
             "staged_copies": total_envs * e2e_steps / (single_copy_ms * 1e-3),
             "zero_copy": total_envs * e2e_steps / (single_zc_ms * 1e-3)}
+        line["e2e"]["int32_actions"] = {
+            "value": total_envs * e2e_steps / (i32_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 4 * envs,
+            "note": "same loop fed int32 actions (half the host->device bytes): the int64 loop is bound by the PCIe copies -- an "
+                    "8-step slab moves 4 MiB in and 2.5 MiB out, ~100 us with both directions busy (tools/pcie_probe.py: 42 + 26 "
+                    "GB/s concurrently) against 70 us of kernels"}
         line["e2e"]["full_d2h"] = {
             "value": total_envs * full_steps / (full_ms * 1e-3), "unit": UNIT, "steps": full_steps,
             "d2h_bytes_per_step": (5 + 9 * wl.cells) * envs,

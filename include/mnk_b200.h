@@ -104,6 +104,21 @@ int mnk_step(const mnk_state_t* st, const void* actions, const int64_t* idx, int
              float* rewards, uint8_t* dones, float* obs, uint8_t* mask, int32_t* illegal,
              uint32_t flags, void* stream);
 
+/* `steps` (<= MNK_MAX_SLAB_STEPS) consecutive dense steps of ALL envs in ONE launch: exactly `steps` calls of
+ * mnk_step(st, actions + i * action_stride, NULL, num_envs, ...) in a row -- TorchVectorMnkEnv.step K times,
+ * src/env/torch_vector_mnk_env.py:55-84 -- for callers that already hold the actions of several steps (a recorded trace, a
+ * slab of a host pipeline: mnk_step_host_loop).  Envs are independent and a CTA keeps its tile of 32 envs for the whole
+ * launch, so no grid-wide synchronisation is needed between the steps.
+ *   actions         step i reads i64 (i32 with MNK_STEP_ACTIONS_I32) [num_envs] at byte offset i * action_stride
+ *   rewards_dones   step i writes f32 rewards[num_envs] followed by u8 dones[num_envs] at byte offset i * rd_stride
+ *                   (rd_stride >= 5 * num_envs, a multiple of 4)
+ *   obs, mask       NULL, or `steps` device pointers each: where step i materialises its f32 observation / u8 mask (entries
+ *                   may be NULL)
+ *   flags           MNK_STEP_ACTIONS_I32 | MNK_STEP_AUTORESET | MNK_STEP_PDL */
+#define MNK_MAX_SLAB_STEPS 16
+int mnk_step_slab(const mnk_state_t* st, const void* actions, int64_t action_stride, void* rewards_dones, int64_t rd_stride,
+                  int32_t steps, float* const* obs, uint8_t* const* mask, uint32_t flags, void* stream);
+
 /* Same as the dense mnk_step but with HOST buffers (the end-to-end path a caller without device
  * tensors uses): copies host_actions to dev_actions, steps, copies rewards / dones back and
  * SYNCHRONISES the stream.  host_* should be pinned.  dev_* are caller-owned scratch:

@@ -33,22 +33,16 @@ reset_kernel(mnk_state_t st, const int64_t* __restrict__ idx, long long count) {
 // ------------------------------------------------------------------------------------------------
 // dense step (+ optional observation / mask materialisation, auto-reset, strict accounting)
 // ------------------------------------------------------------------------------------------------
+// one dense step of this CTA's tile of 32 envs (shared by the one-step and the slab kernel)
 template <class G, bool ACT32>
-__global__ void __launch_bounds__(tile_cta_threads<G>())
-step_dense_kernel(G g, mnk_state_t st, const void* __restrict__ actions, float* __restrict__ rewards,
-                  u8* __restrict__ dones, float* __restrict__ obs, u8* __restrict__ mask,
-                  int32_t* __restrict__ illegal, u32 flags) {
-    __shared__ u32 tile_smem[TileStream<G>::kWords];
+MNK_DEV void step_dense_tile(const G& g, const mnk_state_t& st, const void* __restrict__ actions, float* __restrict__ rewards,
+                             u8* __restrict__ dones, float* __restrict__ obs, u8* __restrict__ mask,
+                             int32_t* __restrict__ illegal, u32 flags, u32* tile_smem) {
     const int lane = threadIdx.x & 31;
     const long long e0 = (long long)blockIdx.x * kTileEnvs;
     const int tile_envs = (int)min((long long)kTileEnvs, st.num_envs - e0);
     const bool emit = obs != nullptr || mask != nullptr;
     const bool stream = emit && tile_streams<G>(tile_envs, obs, mask);   // block-uniform
-    // Programmatic dependent launch (MNK_STEP_PDL): let the next step's CTAs become resident while this grid
-    // drains, and do not touch anything the previous step wrote before it has completed.  Both are no-ops
-    // for a plain launch.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     u64 obsd[G::NWD];
     u64 legd[G::NWL];
     const int warp = threadIdx.x >> 5;
@@ -86,6 +80,47 @@ step_dense_kernel(G g, mnk_state_t st, const void* __restrict__ actions, float* 
         else build_legal_view(g, s, false, legd);
     }
     if (stream) emit_block_stream_any(g, tile_smem, e0, obsd, legd, obs, mask, 1, 2);
+}
+
+template <class G, bool ACT32>
+__global__ void __launch_bounds__(tile_cta_threads<G>())
+step_dense_kernel(G g, mnk_state_t st, const void* __restrict__ actions, float* __restrict__ rewards,
+                  u8* __restrict__ dones, float* __restrict__ obs, u8* __restrict__ mask,
+                  int32_t* __restrict__ illegal, u32 flags) {
+    __shared__ u32 tile_smem[TileStream<G>::kWords];
+    // Programmatic dependent launch (MNK_STEP_PDL): let the next step's CTAs become resident while this grid
+    // drains, and do not touch anything the previous step wrote before it has completed.  Both are no-ops
+    // for a plain launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    step_dense_tile<G, ACT32>(g, st, actions, rewards, dones, obs, mask, illegal, flags, tile_smem);
+}
+
+// A SLAB of consecutive dense steps in ONE launch (mnk_step_slab): envs are independent and a CTA owns its tile of 32
+// for the whole launch, so step s + 1 of a tile only needs step s of the same tile -- a block barrier, not a grid-wide
+// one.  Same device work as `steps` launches of step_dense_kernel (each step materialises its own observation / mask),
+// one launch's worth of host work and no fill / drain between the steps.
+constexpr int kMaxSlabSteps = MNK_MAX_SLAB_STEPS;
+struct SlabArgs {
+    int steps;
+    long long action_stride, rd_stride;      // bytes between consecutive steps' action batches / reward + done blocks
+    float* obs[kMaxSlabSteps];
+    u8* mask[kMaxSlabSteps];
+};
+
+template <class G, bool ACT32>
+__global__ void __launch_bounds__(tile_cta_threads<G>())
+step_dense_slab_kernel(G g, mnk_state_t st, const char* __restrict__ actions, char* __restrict__ rd, SlabArgs sa, u32 flags) {
+    __shared__ u32 tile_smem[TileStream<G>::kWords];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int s = 0; s < sa.steps; ++s) {
+        char* block = rd + (size_t)s * sa.rd_stride;
+        step_dense_tile<G, ACT32>(g, st, actions + (size_t)s * sa.action_stride, reinterpret_cast<float*>(block),
+                                  reinterpret_cast<u8*>(block) + 4 * (size_t)st.num_envs, sa.obs[s], sa.mask[s], nullptr, flags,
+                                  tile_smem);
+        __syncthreads();      // the tile's state written by this step is visible to every warp of the CTA; staging reusable
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -287,6 +322,46 @@ int mnk_pack_boards(const mnk_state_t* st, const float* boards, void* stream) {
     return mnk_dispatch_geom(*st, [&](auto g) {
         pack_kernel<<<mnk_tile_blocks(st->num_envs), kTileThreads, 0, s>>>(g, *st, boards);
         return mnk_launch_status();
+    });
+}
+
+int mnk_step_slab(const mnk_state_t* st, const void* actions, int64_t action_stride, void* rewards_dones, int64_t rd_stride,
+                  int32_t steps, float* const* obs, uint8_t* const* mask, uint32_t flags, void* stream) {
+    if (int rc = mnk_check_state(st)) return rc;
+    if (actions == nullptr || rewards_dones == nullptr) return MNK_ERR_NULL;
+    if (steps < 0 || steps > kMaxSlabSteps || rd_stride < 5 * st->num_envs || (rd_stride & 3) != 0) return MNK_ERR_ARG;
+    if (action_stride < (int64_t)((flags & MNK_STEP_ACTIONS_I32) ? 4 : 8) * st->num_envs) return MNK_ERR_ARG;
+    if (steps == 0 || st->num_envs == 0) return MNK_OK;
+    SlabArgs sa;
+    sa.steps = steps; sa.action_stride = action_stride; sa.rd_stride = rd_stride;
+    bool views = false;
+    for (int i = 0; i < kMaxSlabSteps; ++i) {
+        sa.obs[i] = (obs != nullptr && i < steps) ? obs[i] : nullptr;
+        sa.mask[i] = (mask != nullptr && i < steps) ? mask[i] : nullptr;
+        if (reinterpret_cast<uintptr_t>(sa.obs[i]) & 7u) return MNK_ERR_ALIGN;
+        views = views || sa.obs[i] != nullptr || sa.mask[i] != nullptr;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool act32 = (flags & MNK_STEP_ACTIONS_I32) != 0;
+    return mnk_dispatch_geom(*st, [&](auto g) {
+        using G = decltype(g);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(mnk_cta_tiles(st->num_envs));
+        cfg.blockDim = dim3(views ? tile_cta_threads<G>() : 32);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (flags & MNK_STEP_PDL) ? 1 : 0;
+        const mnk_state_t stv = *st;
+        const char* a = static_cast<const char*>(actions);
+        char* rd = static_cast<char*>(rewards_dones);
+        cudaError_t e;
+        if (act32) e = cudaLaunchKernelEx(&cfg, step_dense_slab_kernel<G, true>, g, stv, a, rd, sa, flags);
+        else e = cudaLaunchKernelEx(&cfg, step_dense_slab_kernel<G, false>, g, stv, a, rd, sa, flags);
+        return e == cudaSuccess ? mnk_launch_status() : (int)e;
     });
 }
 

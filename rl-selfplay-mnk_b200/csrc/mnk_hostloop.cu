@@ -6,8 +6,8 @@
 // pinned host memory -- a recorded game trace, an evaluation script, a host-side policy that works a slab ahead --
 // as a three-stage pipeline over SLABS of `slab_steps` steps:
 //
-//     copy-in stream :  H2D actions of slab i+1           (one cudaMemcpyAsync per slab)
-//     caller's stream:  slab_steps step kernels of slab i (programmatic dependent launch between them)
+//     copy-in stream :  H2D actions of slab i+1           (one cudaMemcpyAsync per slab, queued a slab ahead of the host)
+//     caller's stream:  the steps of slab i               (ONE launch: mnk_step_slab loops over a tile's steps)
 //     copy-out stream:  D2H rewards + dones of slab i-1   (one cudaMemcpyAsync per slab; optionally every
 //                                                          step's f32 observation + bool mask as well)
 //
@@ -94,30 +94,47 @@ int mnk_step_host_loop(const mnk_state_t* st, const mnk_host_loop_t* job, void* 
     cudaError_t e = cudaSuccess;
     auto fail = [&](cudaError_t err) { if (rc == MNK_OK && err != cudaSuccess) rc = (int)err; return err != cudaSuccess; };
 
+    // copy-in of slab j: its device buffer's previous tenant (slab j-2) must have been consumed by its kernels -- a
+    // stream-side wait, so the copy is queued a whole slab ahead of the host (it used to be queued only after the host had
+    // waited for slab j-2's results, which serialised copy-in behind copy-out: 140 us per 8-step slab instead of ~80)
+    auto copy_in = [&](int64_t j) -> bool {
+        const int b = (int)(j & 1);
+        const int64_t t0 = j * S, cnt = (K - t0 < S) ? (K - t0) : S;
+        char* d_act = static_cast<char*>(job->dev_actions) + (size_t)b * S * abytes;
+        if (j >= 2 && fail(cudaStreamWaitEvent(p->in, p->compute_done[b], 0))) return false;
+        if (fail(cudaMemcpyAsync(d_act, static_cast<const char*>(job->host_actions) + (size_t)t0 * abytes, (size_t)cnt * abytes,
+                                 cudaMemcpyHostToDevice, p->in)))
+            return false;
+        return !fail(cudaEventRecord(p->in_done[b], p->in));
+    };
+    copy_in(0);
     for (int64_t i = 0; i < slabs && rc == MNK_OK; ++i) {
         const int b = (int)(i & 1);
         const int64_t t0 = i * S, cnt = (K - t0 < S) ? (K - t0) : S;
         char* d_act = static_cast<char*>(job->dev_actions) + (size_t)b * S * abytes;
         char* d_rd = static_cast<char*>(job->dev_rd) + (size_t)b * S * rbytes;
-        // ---- copy-in: this buffer's previous tenant (slab i-2) must have been consumed by its kernels
-        if (i >= 2 && fail(cudaStreamWaitEvent(p->in, p->compute_done[b], 0))) break;
-        if (fail(cudaMemcpyAsync(d_act, static_cast<const char*>(job->host_actions) + (size_t)t0 * abytes, (size_t)cnt * abytes,
-                                 cudaMemcpyHostToDevice, p->in)))
-            break;
-        if (fail(cudaEventRecord(p->in_done[b], p->in))) break;
         // ---- compute: needs the actions; its result slab's previous tenant must have left for the host
         if (fail(cudaStreamWaitEvent(s, p->in_done[b], 0))) break;
         if (i >= 2 && fail(cudaStreamWaitEvent(s, p->out_done[b], 0))) break;
-        for (int64_t j = 0; j < cnt && rc == MNK_OK; ++j) {
-            const int64_t t = t0 + j;
-            float* rewards = reinterpret_cast<float*>(d_rd + (size_t)j * rbytes);
-            uint8_t* dones = reinterpret_cast<uint8_t*>(d_rd + (size_t)j * rbytes + 4 * n);
-            float* obs = want_views ? job->obs_ring[t % job->ring] : nullptr;
-            uint8_t* mask = want_views ? job->mask_ring[t % job->ring] : nullptr;
-            rc = mnk_step(st, d_act + (size_t)j * abytes, nullptr, st->num_envs, rewards, dones, obs, mask, nullptr, step_flags, s);
+        // the slab's steps: ONE launch per MNK_MAX_SLAB_STEPS steps (mnk_step_slab: a tile's steps only depend on the same
+        // tile, so the kernel loops over them), not one launch per step -- the host side of a slab is then a launch, two
+        // copies and five event operations whatever the slab length
+        for (int64_t j0 = 0; j0 < cnt && rc == MNK_OK; j0 += MNK_MAX_SLAB_STEPS) {
+            const int part = (int)((cnt - j0 < MNK_MAX_SLAB_STEPS) ? (cnt - j0) : MNK_MAX_SLAB_STEPS);
+            float* obs[MNK_MAX_SLAB_STEPS];
+            uint8_t* mask[MNK_MAX_SLAB_STEPS];
+            for (int j = 0; j < part; ++j) {
+                const int64_t t = t0 + j0 + j;
+                obs[j] = want_views ? job->obs_ring[t % job->ring] : nullptr;
+                mask[j] = want_views ? job->mask_ring[t % job->ring] : nullptr;
+            }
+            rc = mnk_step_slab(st, d_act + (size_t)j0 * abytes, (int64_t)abytes, d_rd + (size_t)j0 * rbytes, (int64_t)rbytes, part,
+                               obs, mask, step_flags, s);
         }
         if (rc != MNK_OK) break;
         if (fail(cudaEventRecord(p->compute_done[b], s))) break;
+        // ---- copy-in of the NEXT slab (its buffer was last read by slab i-1, whose completion event is already recorded)
+        if (i + 1 < slabs && !copy_in(i + 1)) break;
         // ---- copy-out
         if (fail(cudaStreamWaitEvent(p->out, p->compute_done[b], 0))) break;
         if (fail(cudaMemcpyAsync(static_cast<char*>(job->host_rd) + (size_t)t0 * rbytes, d_rd, (size_t)cnt * rbytes,

@@ -114,6 +114,7 @@ SIGNATURES = {
     "mnk_reset": (_I32, [_ST, _VP, _I64, _VP]),
     "mnk_observe": (_I32, [_ST, _VP, _VP, _VP, _I32, _VP]),
     "mnk_step": (_I32, [_ST, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
+    "mnk_step_slab": (_I32, [_ST, _VP, _I64, _VP, _I64, _I32, _VP, _VP, _U32, _VP]),
     "mnk_step_host": (_I32, [_ST, _VP, _VP, _VP, _VP, _VP, _VP, _U32, _VP]),
     "mnk_host_pipe_create": (_I32, [ctypes.POINTER(ctypes.c_void_p)]),
     "mnk_host_pipe_destroy": (_I32, [_VP]),

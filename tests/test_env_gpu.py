@@ -378,3 +378,57 @@ def test_strict_counters_of_the_c_abi():
     rc = _lib.lib().mnk_step(env._stp, torch.tensor([5, 1], device=DEV).data_ptr(), idx.data_ptr(), 2, rewards.data_ptr(),
                              dones.data_ptr(), None, None, illegal.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
     assert rc == 0 and illegal.tolist()[0] == 1 and 0x7FFFFFFF - illegal.tolist()[1] == 3
+
+
+@pytest.mark.parametrize("m,n,k,ne", [(9, 9, 5, 1000), (3, 3, 3, 77), (13, 13, 5, 65), (7, 11, 4, 50), (19, 19, 5, 33)], ids=str)
+def test_step_slab_equals_consecutive_steps(m, n, k, ne):
+    """mnk_step_slab (K dense steps in one launch, the kernel looping over a tile's steps) against K calls of mnk_step on a
+    twin env: bit-identical state, rewards, dones and every step's materialised observation / mask -- static and dynamic
+    geometries, tail tiles, auto-reset, with and without materialisation, int32 actions."""
+    import ctypes
+    from mnk_b200 import TorchVectorMnkEnv, _lib
+    L = _lib.lib()
+    K = 11
+    for materialise, act32 in ((True, False), (False, True)):
+        a_env = TorchVectorMnkEnv(m, n, k, ne, device=DEV)
+        b_env = TorchVectorMnkEnv(m, n, k, ne, device=DEV)
+        a_env.reset(), b_env.reset()
+        for t in range(m * n // 3):                          # a mid-game start, identical in both
+            act = a_env.random_legal_actions(3, t)
+            a_env.step_autoreset(act, materialise=False), b_env.step_autoreset(act, materialise=False)
+        # K action batches generated by playing a third twin forward (legal at every step)
+        probe = TorchVectorMnkEnv(m, n, k, ne, device=DEV)
+        probe._bits.copy_(a_env._bits), probe._meta.copy_(a_env._meta)
+        acts = []
+        for t in range(K):
+            act = probe.random_legal_actions(9, t)
+            acts.append(act)
+            probe.step_autoreset(act, materialise=False)
+        acts = torch.stack(acts).to(torch.int32 if act32 else torch.int64).contiguous()
+        want = []
+        for t in range(K):
+            obs, r, d = a_env.step_autoreset(acts[t].long(), materialise=materialise)
+            want.append((r.clone(), d.clone(), None if not materialise else obs["observation"].clone(),
+                         None if not materialise else obs["action_mask"].clone()))
+        rd_stride = (5 * ne + 3) // 4 * 4 + 8
+        rd = torch.zeros(K * rd_stride, dtype=torch.uint8, device=DEV)
+        obs_out = [torch.empty((ne, 2, m, n), dtype=torch.float32, device=DEV) for _ in range(K)]
+        mask_out = [torch.empty((ne, m * n), dtype=torch.bool, device=DEV) for _ in range(K)]
+        PtrArr = ctypes.c_void_p * K
+        flags = _lib.STEP_AUTORESET | (_lib.STEP_ACTIONS_I32 if act32 else 0)
+        b_env._fold_mirrors()
+        _lib.check(L.mnk_step_slab(ctypes.byref(b_env._st), acts.data_ptr(), acts.stride(0) * acts.element_size(), rd.data_ptr(),
+                                   rd_stride, K, PtrArr(*[o.data_ptr() for o in obs_out]) if materialise else None,
+                                   PtrArr(*[o.data_ptr() for o in mask_out]) if materialise else None, flags,
+                                   torch.cuda.current_stream().cuda_stream), "mnk_step_slab")
+        torch.cuda.synchronize()
+        assert torch.equal(a_env._bits, b_env._bits) and torch.equal(a_env._meta, b_env._meta)
+        for t in range(K):
+            block = rd[t * rd_stride:(t + 1) * rd_stride]
+            assert torch.equal(block[:4 * ne].view(torch.float32), want[t][0]), t
+            assert torch.equal(block[4 * ne:5 * ne].bool(), want[t][1]), t
+            if materialise:
+                assert torch.equal(obs_out[t], want[t][2]) and torch.equal(mask_out[t], want[t][3]), t
+    with pytest.raises(ValueError):
+        _lib.check(L.mnk_step_slab(ctypes.byref(b_env._st), acts.data_ptr(), 8 * ne, rd.data_ptr(), rd_stride, 17, None, None, 0,
+                                   torch.cuda.current_stream().cuda_stream), "mnk_step_slab")
