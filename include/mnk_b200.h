@@ -140,13 +140,16 @@ typedef struct mnk_host_loop {
     void* host_rd;              /* pinned  [steps][5*num_envs] bytes: per step f32 rewards[num_envs], u8 dones[num_envs] */
     float* host_obs;            /* NULL, or pinned f32 [steps][num_envs][2][m][n]: also bring every observation home */
     uint8_t* host_mask;         /* NULL, or pinned u8  [steps][num_envs][m*n]                                     */
-    void* dev_actions;          /* device scratch [2][slab_steps][num_envs] actions                               */
-    void* dev_rd;               /* device scratch [2][slab_steps][5*num_envs] bytes                               */
+    void* dev_actions;          /* device scratch [buffers][slab_steps][num_envs] actions                         */
+    void* dev_rd;               /* device scratch [buffers][slab_steps][5*num_envs] bytes                         */
     float* const* obs_ring;     /* host array of `ring` device pointers f32[num_envs][2][m][n]: step t materialises */
     uint8_t* const* mask_ring;  /*   its observation / mask into slot t % ring (ring == 0: packed mode, no views) */
-    int32_t ring;               /* >= 2 * slab_steps when host_obs / host_mask are set                            */
+    int32_t ring;               /* >= buffers * slab_steps when host_obs / host_mask are set                      */
     int64_t steps, slab_steps;
+    int32_t buffers;            /* slabs in flight, 2 .. MNK_HOST_LOOP_MAX_BUFFERS (0 = 2): with 3 the host waits for slab  */
+                                /* i-2 after queuing slab i, so a slow copy-out no longer delays the next slab's kernels  */
 } mnk_host_loop_t;
+#define MNK_HOST_LOOP_MAX_BUFFERS 4
 
 /* Streams + events of the pipeline, owned by the caller (create once, reuse across calls on the same device). */
 int mnk_host_pipe_create(void** pipe);

@@ -19,13 +19,13 @@
 
 struct mnk_host_pipe {
     cudaStream_t in = nullptr, out = nullptr;
-    cudaEvent_t in_done[2] = {nullptr, nullptr}, compute_done[2] = {nullptr, nullptr}, out_done[2] = {nullptr, nullptr};
+    cudaEvent_t in_done[MNK_HOST_LOOP_MAX_BUFFERS] = {}, compute_done[MNK_HOST_LOOP_MAX_BUFFERS] = {}, out_done[MNK_HOST_LOOP_MAX_BUFFERS] = {};
     int device = -1;
 };
 
 static void pipe_free(mnk_host_pipe* p) {
     if (p == nullptr) return;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < MNK_HOST_LOOP_MAX_BUFFERS; ++i) {
         if (p->in_done[i]) cudaEventDestroy(p->in_done[i]);
         if (p->compute_done[i]) cudaEventDestroy(p->compute_done[i]);
         if (p->out_done[i]) cudaEventDestroy(p->out_done[i]);
@@ -44,7 +44,7 @@ int mnk_host_pipe_create(void** pipe) {
     cudaError_t e = cudaGetDevice(&p->device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->out, cudaStreamNonBlocking);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    for (int i = 0; i < MNK_HOST_LOOP_MAX_BUFFERS && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&p->in_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->compute_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->out_done[i], cudaEventDisableTiming);
@@ -68,12 +68,13 @@ int mnk_step_host_loop(const mnk_state_t* st, const mnk_host_loop_t* job, void* 
         job->dev_rd == nullptr)
         return MNK_ERR_NULL;
     const int64_t K = job->steps, S = job->slab_steps;
-    if (K < 0 || S < 1 || job->ring < 0) return MNK_ERR_ARG;
+    const int NB = job->buffers == 0 ? 2 : job->buffers;           // slabs in flight
+    if (K < 0 || S < 1 || job->ring < 0 || NB < 2 || NB > MNK_HOST_LOOP_MAX_BUFFERS) return MNK_ERR_ARG;
     const bool want_views = job->ring > 0;
     if (want_views && (job->obs_ring == nullptr || job->mask_ring == nullptr)) return MNK_ERR_NULL;
     const bool copy_views = job->host_obs != nullptr || job->host_mask != nullptr;
-    // a ring slot is rewritten `ring` steps later; with the views copied out, up to two slabs are in flight
-    if (copy_views && (!want_views || job->ring < 2 * S)) return MNK_ERR_ARG;
+    // a ring slot is rewritten `ring` steps later; with the views copied out, up to NB slabs are in flight
+    if (copy_views && (!want_views || job->ring < NB * S)) return MNK_ERR_ARG;
     if (K == 0 || st->num_envs == 0) return MNK_OK;
 
     mnk_host_pipe* p = static_cast<mnk_host_pipe*>(pipe);
@@ -98,24 +99,25 @@ int mnk_step_host_loop(const mnk_state_t* st, const mnk_host_loop_t* job, void* 
     // stream-side wait, so the copy is queued a whole slab ahead of the host (it used to be queued only after the host had
     // waited for slab j-2's results, which serialised copy-in behind copy-out: 140 us per 8-step slab instead of ~80)
     auto copy_in = [&](int64_t j) -> bool {
-        const int b = (int)(j & 1);
+        if (j >= slabs) return true;
+        const int b = (int)(j % NB);
         const int64_t t0 = j * S, cnt = (K - t0 < S) ? (K - t0) : S;
         char* d_act = static_cast<char*>(job->dev_actions) + (size_t)b * S * abytes;
-        if (j >= 2 && fail(cudaStreamWaitEvent(p->in, p->compute_done[b], 0))) return false;
+        if (j >= NB && fail(cudaStreamWaitEvent(p->in, p->compute_done[b], 0))) return false;
         if (fail(cudaMemcpyAsync(d_act, static_cast<const char*>(job->host_actions) + (size_t)t0 * abytes, (size_t)cnt * abytes,
                                  cudaMemcpyHostToDevice, p->in)))
             return false;
         return !fail(cudaEventRecord(p->in_done[b], p->in));
     };
-    copy_in(0);
+    for (int j = 0; j < NB - 1; ++j) copy_in(j);
     for (int64_t i = 0; i < slabs && rc == MNK_OK; ++i) {
-        const int b = (int)(i & 1);
+        const int b = (int)(i % NB);
         const int64_t t0 = i * S, cnt = (K - t0 < S) ? (K - t0) : S;
         char* d_act = static_cast<char*>(job->dev_actions) + (size_t)b * S * abytes;
         char* d_rd = static_cast<char*>(job->dev_rd) + (size_t)b * S * rbytes;
         // ---- compute: needs the actions; its result slab's previous tenant must have left for the host
         if (fail(cudaStreamWaitEvent(s, p->in_done[b], 0))) break;
-        if (i >= 2 && fail(cudaStreamWaitEvent(s, p->out_done[b], 0))) break;
+        if (i >= NB && fail(cudaStreamWaitEvent(s, p->out_done[b], 0))) break;
         // the slab's steps: ONE launch per MNK_MAX_SLAB_STEPS steps (mnk_step_slab: a tile's steps only depend on the same
         // tile, so the kernel loops over them), not one launch per step -- the host side of a slab is then a launch, two
         // copies and five event operations whatever the slab length
@@ -133,8 +135,8 @@ int mnk_step_host_loop(const mnk_state_t* st, const mnk_host_loop_t* job, void* 
         }
         if (rc != MNK_OK) break;
         if (fail(cudaEventRecord(p->compute_done[b], s))) break;
-        // ---- copy-in of the NEXT slab (its buffer was last read by slab i-1, whose completion event is already recorded)
-        if (i + 1 < slabs && !copy_in(i + 1)) break;
+        // ---- copy-in NB - 1 slabs ahead (that buffer was last read by slab i-1, whose completion event is already recorded)
+        if (!copy_in(i + NB - 1)) break;
         // ---- copy-out
         if (fail(cudaStreamWaitEvent(p->out, p->compute_done[b], 0))) break;
         if (fail(cudaMemcpyAsync(static_cast<char*>(job->host_rd) + (size_t)t0 * rbytes, d_rd, (size_t)cnt * rbytes,
@@ -153,8 +155,8 @@ int mnk_step_host_loop(const mnk_state_t* st, const mnk_host_loop_t* job, void* 
             if (rc != MNK_OK) break;
         }
         if (fail(cudaEventRecord(p->out_done[b], p->out))) break;
-        // ---- the one host wait per slab: the PREVIOUS slab's results are now in host memory
-        if (i >= 1 && fail(cudaEventSynchronize(p->out_done[b ^ 1]))) break;
+        // ---- the one host wait per slab: the results of slab i - (NB - 1) are now in host memory
+        if (i >= NB - 1 && fail(cudaEventSynchronize(p->out_done[(i - (NB - 1)) % NB]))) break;
     }
     // drain: last slab's copy-out (also orders everything before the caller's next use of its stream / buffers)
     e = cudaStreamSynchronize(p->out);

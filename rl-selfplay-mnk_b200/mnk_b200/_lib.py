@@ -43,7 +43,7 @@ class MnkHostLoop(ctypes.Structure):
     _fields_ = [("host_actions", ctypes.c_void_p), ("host_rd", ctypes.c_void_p), ("host_obs", ctypes.c_void_p),
                 ("host_mask", ctypes.c_void_p), ("dev_actions", ctypes.c_void_p), ("dev_rd", ctypes.c_void_p),
                 ("obs_ring", ctypes.POINTER(ctypes.c_void_p)), ("mask_ring", ctypes.POINTER(ctypes.c_void_p)),
-                ("ring", ctypes.c_int32), ("steps", ctypes.c_int64), ("slab_steps", ctypes.c_int64)]
+                ("ring", ctypes.c_int32), ("steps", ctypes.c_int64), ("slab_steps", ctypes.c_int64), ("buffers", ctypes.c_int32)]
 
 
 class MnkHeadsWeights(ctypes.Structure):

@@ -289,7 +289,7 @@ class TorchVectorMnkEnv:
 
     def step_host_loop(self, host_actions: torch.Tensor, host_out: torch.Tensor, slab_steps: int = 4, autoreset: bool = False,
                        ring: Optional[Tuple[list, list]] = None, host_obs: Optional[torch.Tensor] = None,
-                       host_mask: Optional[torch.Tensor] = None):
+                       host_mask: Optional[torch.Tensor] = None, buffers: int = 3):
         """K dense steps in ONE call of the C ABI (mnk_step_host_loop): `host_actions` pinned int64|int32 [K, N],
         `host_out` pinned uint8 [K, 5*N] (per step f32 rewards then bool dones).  The library pipelines slabs of
         `slab_steps` steps -- H2D of the next slab | the step kernels | D2H of the previous slab -- with one copy per
@@ -312,10 +312,13 @@ class TorchVectorMnkEnv:
         elif host_actions.dtype != torch.long:
             raise ValueError("step_host_loop: actions must be int64 or int32")
         slab_steps = max(1, min(int(slab_steps), steps)) if steps else 1
-        key = (slab_steps, host_actions.dtype)
-        if getattr(self, "_loop_key", None) != key:      # device slabs (double-buffered) and the stream / event pipe
-            self._loop_dev_actions = torch.empty((2, slab_steps, n), dtype=host_actions.dtype, device=self._dev)
-            self._loop_dev_rd = torch.empty((2, slab_steps, 5 * n), dtype=torch.uint8, device=self._dev)
+        buffers = max(2, min(int(buffers), 4))
+        if ring is not None and (host_obs is not None or host_mask is not None):
+            buffers = max(2, min(buffers, len(ring[0]) // slab_steps))       # the views of every slab in flight stay in the ring
+        key = (slab_steps, host_actions.dtype, buffers)
+        if getattr(self, "_loop_key", None) != key:      # device slabs (`buffers` deep) and the stream / event pipe
+            self._loop_dev_actions = torch.empty((buffers, slab_steps, n), dtype=host_actions.dtype, device=self._dev)
+            self._loop_dev_rd = torch.empty((buffers, slab_steps, 5 * n), dtype=torch.uint8, device=self._dev)
             self._loop_key = key
         if getattr(self, "_loop_pipe", None) is None:
             pipe = ctypes.c_void_p()
@@ -338,7 +341,7 @@ class TorchVectorMnkEnv:
             job.obs_ring, job.mask_ring, job.ring = arr_o, arr_m, cnt
         else:
             job.ring = 0
-        job.steps, job.slab_steps = steps, slab_steps
+        job.steps, job.slab_steps, job.buffers = steps, slab_steps, buffers
         self._call(self._L.mnk_step_host_loop, ctypes.byref(job), self._loop_pipe, flags)
         self._refresh_mirrors()
         out = host_out.reshape(-1)[: steps * 5 * n].view(steps, 5 * n)
