@@ -485,6 +485,33 @@ def bench_env_workload(ctx: Ctx, wl: Workload, args, primary: bool):
     ms_eager = ctx.reduce([ev0.elapsed_time(ev1)], "max")[0]
     verified = verified and env.state_checksum() == want_digest
 
+    # ---- slab launches (for the record): the same K steps as ceil(K / 16) launches of mnk_step_slab ----------
+    ms_slab = None
+    if primary and actions.is_contiguous():
+        import ctypes
+        slab_rd = torch.empty((K, 5 * envs + 8), dtype=torch.uint8, device=dev)
+        slab_calls = []
+        for t0 in range(W, total, 16):
+            cnt = min(16, total - t0)
+            PtrArr = ctypes.c_void_p * cnt
+            slab_calls.append((actions[t0].data_ptr(), slab_rd[t0 - W].data_ptr(), cnt,
+                               PtrArr(*[obs_ring[t % ring].data_ptr() for t in range(t0, t0 + cnt)]),
+                               PtrArr(*[mask_ring[t % ring].data_ptr() for t in range(t0, t0 + cnt)])))
+        g_slab = torch.cuda.CUDAGraph()
+        side.wait_stream(torch.cuda.current_stream())
+        to_warm()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g_slab, stream=side):
+                for a_ptr, rd_ptr, cnt, po, pm in slab_calls:
+                    _lib.check(L.mnk_step_slab(env._stp, a_ptr, actions.stride(0) * 8, rd_ptr, slab_rd.stride(0), cnt, po, pm, flags,
+                                               side.cuda_stream), "mnk_step_slab")
+        torch.cuda.current_stream().wait_stream(side)
+        g_slab.replay()
+        torch.cuda.synchronize()
+        per_s, _ = timed_replays(g_slab, min(R, 10))
+        ms_slab = statistics.median(per_s)
+        verified = verified and env.state_checksum() == want_digest
+
     # ---- packed mode: the same K steps without materialising observation / mask -----------
     ms_packed = None
     if primary:
@@ -585,6 +612,12 @@ def bench_env_workload(ctx: Ctx, wl: Workload, args, primary: bool):
         "method": {"launch": f"one CUDA graph of {K} step_dense_kernel nodes{'' if args.no_pdl else ' with programmatic dependent launch edges'}, "
                              f"replayed {R} times (state restored between replays, outside the timed span); value = median replay",
                    "eager_launches_value": total_envs * K / (ms_eager * 1e-3)},
+        "slab_launches": None if ms_slab is None else {
+            "value": total_envs * K / (ms_slab * 1e-3), "unit": UNIT, "launches": -(-K // 16),
+            "hbm_frac": wl.alg_bytes * envs / (1e3 * ms_slab / K * 1e-6) / 1e9 / measured_peak("hbm_gbs")[0],
+            "note": "for the record, NOT the headline: the same K steps (same actions, same per-step outputs) as ceil(K / 16) launches "
+                    "of mnk_step_slab -- a CTA loops over its tile's steps, so there is no per-step launch fill / drain; only "
+                    "usable when the actions of several steps are known in advance (mnk_step_host_loop uses it)"},
         "timing": {"replays": R, "ms_median": ms, "ms_min": min(per_replay), "ms_max": max(per_replay), "ms_first": per_replay[0],
                    "value_at_min": total_envs * K / (min(per_replay) * 1e-3), "value_at_max": total_envs * K / (max(per_replay) * 1e-3),
                    "whole_sequence_ms": whole_ms},
