@@ -64,7 +64,7 @@ struct Cfg {
     static constexpr int oLn1 = 0, oBqkv = 2 * DP, oBo = oBqkv + 3 * QP, oLn2 = oBo + DP, oB1 = oLn2 + 2 * DP, oB2 = oB1 + F;
     static constexpr int kLayerParams = oB2 + DP;
     static_assert(DP <= kWorkCol && kWorkCol + 3 * QP <= kTmemCols && kWorkCol + F <= kTmemCols, "tensor memory plan");
-    static_assert(kWorkCol + 128 + QP <= kTmemCols, "scores + attention output");
+    static_assert(kWorkCol + 256 + QP <= kTmemCols, "two score buffers + attention output");
     static_assert(DH <= 16 && DP % 16 == 0 && F % (16 * NSPLIT) == 0 && (3 * QP) % (16 * NSPLIT) == 0, "shapes");
 };
 
@@ -413,18 +413,20 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
 #ifndef TF_EXP_HEADS          // timing experiments only (wrong results): how many heads run
 #define TF_EXP_HEADS NH
 #endif
+        // The scores of head h + 1 are issued together with O_h = P_h V_h (two score buffers in tensor memory): one MMA
+        // round trip per head instead of two.
+        if (warp == kMmaWarp) {
+            if (elect_one()) {
+                issue_gemm(tmem + (u32)kWorkCol, smem_u32(qbuf), 1, smem_u32(kbuf), 128, false);
+                umma_commit(&sm.mma_bar);
+            }
+            __syncwarp();
+        }
+        wait_mma();
+        TF_STAMP();
 #pragma unroll 1
         for (int h = 0; h < TF_EXP_HEADS; ++h) {
-            if (warp == kMmaWarp) {
-                if (elect_one()) {
-                    issue_gemm(tmem + (u32)kWorkCol, smem_u32(qbuf) + (u32)(h * 2 * 2048), 1, smem_u32(kbuf) + (u32)(h * 2 * 2048), 128, false);
-                    umma_commit(&sm.mma_bar);
-                }
-                __syncwarp();
-            }
-            wait_mma();
-            TF_STAMP();
-        TF_STAMP();
+            const u32 s_col = (u32)(kWorkCol + 128 * (h & 1));          // this head's score columns
 #ifdef TF_EXP_NO_SOFTMAX
             if (false) {
 #else
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
                 float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};      // four independent chains
                 {
                     u32 v[kSC];
-                    tmem_ld_cols<kSC>(t_row + (u32)(kWorkCol + kSC * part), v);
+                    tmem_ld_cols<kSC>(t_row + s_col + (u32)(kSC * part), v);
 #pragma unroll
                     for (int c8 = 0; c8 < kSC / 8; ++c8) {
                         // keys of no board that has a row in this warp: nothing to compute (warp-uniform branch) -- at 9x9 a
@@ -523,7 +525,6 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
             }
             phase_sync();
             TF_STAMP();
-        TF_STAMP();
             if (warp == kMmaWarp) {
                 if (elect_one()) {
                     // O_h[128 x 16] = P[128 x 128 keys] V_h: B = V^T_h as [key chunk][16 dims][16 B]
@@ -534,8 +535,11 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
                     for (int ks = 0; ks < TF_EXP_PV_KSTEPS; ++ks) {
                         const u64 a_d = umma_desc(smem_u32(bufA) + (u32)(ks * 2 * 2048), 2048, 128);
                         const u64 b_d = umma_desc(smem_u32(vtbuf) + (u32)(h * K::kVtHead + ks * 2 * K::kVtChunk), K::kVtChunk, 128);
-                        umma_bf16(tmem + (u32)(kWorkCol + 128 + 16 * h), a_d, b_d, idesc, ks != 0);
+                        umma_bf16(tmem + (u32)(kWorkCol + 256 + 16 * h), a_d, b_d, idesc, ks != 0);
                     }
+                    if (h + 1 < NH)
+                        issue_gemm(tmem + (u32)(kWorkCol + 128 * ((h + 1) & 1)), smem_u32(qbuf) + (u32)((h + 1) * 2 * 2048), 1,
+                                   smem_u32(kbuf) + (u32)((h + 1) * 2 * 2048), 128, false);
                     umma_commit(&sm.mma_bar);
                 }
                 __syncwarp();
@@ -545,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) transformer_body_kernel(Params p)
         }
         // ---- attention output -> bufA as the out_proj operand; x += out_proj bias ------------------------------------------
         if (worker) {
-            for_cols<K::QP / kParts>(t_row + (u32)(kWorkCol + 128 + part * (K::QP / kParts)), [&](int rel, const u32* v) {
+            for_cols<K::QP / kParts>(t_row + (u32)(kWorkCol + 256 + part * (K::QP / kParts)), [&](int rel, const u32* v) {
                 const int c0 = part * (K::QP / kParts) + rel;
                 u32 w[4];
 #pragma unroll

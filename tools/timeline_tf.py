@@ -18,9 +18,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 st = fwd._err.cpu().tolist()[1:]
 heads = fwd.heads
-names = ["LN1 -> bufA", "in_proj MMA", "in_proj epilogue (Q, K, V^T)"]
+names = ["LN1 -> bufA", "in_proj MMA", "in_proj epilogue (Q, K, V^T)", "h0 scores MMA"]
 for h in range(heads):
-    names += [f"h{h} scores MMA", None, f"h{h} softmax -> P", None, f"h{h} PV MMA"]
+    names += [f"h{h} softmax -> P", f"h{h} PV MMA (+ scores of h{h + 1})"]
 names += ["O epilogue + out_proj bias", "out_proj MMA", "LN2 -> bufA", "linear1 MMA", "linear1 epilogue + bias", "linear2 MMA"]
 for layer in range(2):
     base = layer * len(names)
