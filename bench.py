@@ -834,6 +834,12 @@ def bench_forwards(ctx: Ctx, args, envs: int):
     for t in range(24):
         env.step_autoreset(env.random_legal_actions(SEED, t), materialise=False)
     peak, peak_src = measured_peak("bf16_tflops_sustained")
+    small = min(envs, 4096)                      # the stock-PyTorch comparison runs on a slice (its activations are large)
+    env_small = TorchVectorMnkEnv(m, n, k, small, device=f"cuda:{ctx.local_rank}")
+    env_small._bits.copy_(env._bits[:, :, :small])
+    env_small._meta.copy_(env._meta[:small])
+    obs_small = env_small.observe()["observation"]
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
     out = {}
     for name, mode in (("resnet_b_s", "eval"), ("resnet_b_s", "train"), ("resnet_b_l", "eval"), ("cnn_b_s", "eval"), ("cnn_b_l", "eval"),
                        ("transformer_b_s", "eval"), ("transformer_b_l", "eval")):
@@ -861,14 +867,28 @@ def bench_forwards(ctx: Ctx, args, envs: int):
         ms = ctx.reduce([e0.elapsed_time(e1) / reps], "max")[0]
         fwd.check_error()
         tf = envs * flops / (ms * 1e-3) / 1e12
+        # the same forward through the stock module on the slice (TF32 allowed, as the reference configures: utils/hardware.py:35-37)
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+        with torch.no_grad():
+            for _ in range(2):
+                net(obs_small, None)
+            e0.record()
+            for _ in range(3):
+                net(obs_small, None)
+            e1.record()
+        torch.cuda.synchronize()
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+        stock_sps = small / (e0.elapsed_time(e1) / 3 * 1e-3)
         out[f"{name}_{mode}"] = {"samples_per_s": envs * ctx.world / (ms * 1e-3), "ms_per_forward": ms, "mflop_per_sample": flops / 1e6,
                                  "useful_tflops_per_gpu": tf, "frac_of_bf16_peak": tf / peak,
-                                 "kernel": type(fwd).__name__ + (" (mnk_resnet_tower_train)" if mode == "train" else "")}
+                                 "kernel": type(fwd).__name__ + (" (mnk_resnet_tower_train)" if mode == "train" else ""),
+                                 "stock_torch_samples_per_s_per_gpu": stock_sps, "x_stock_torch": envs / (ms * 1e-3) / stock_sps}
         del fwd, net
-    del env
+    del env, env_small, obs_small
     torch.cuda.empty_cache()
     return {"metric": "network forward samples/sec (9x9, logits + value from packed bitboards)", "unit": "samples/s", "n_gpus": ctx.world,
             "envs_per_gpu": envs, "dtype": "fp16 operands, fp32 accumulate", "peak_tflops": peak, "peak_source": peak_src,
+            "stock_torch": f"the same module's forward (fp32, TF32 allowed; train mode for the *_train entry) on {small} of the positions",
             "forwards": out}
 
 
