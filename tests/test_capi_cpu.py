@@ -60,6 +60,25 @@ def test_argument_validation_without_gpu():
     with pytest.raises(ValueError):
         _lib.check(_lib.MNK_ERR_GEOM, "x")
     assert b"ok" == L.mnk_error_string(0)
+    # round-2 entry points: the same argument checks, still without a CUDA call
+    a = addr
+    assert L.mnk_step_slab(ctypes.byref(st), None, 32, a, 32, 1, None, None, 0, None) == _lib.MNK_ERR_NULL
+    assert L.mnk_step_slab(ctypes.byref(st), a, 32, a, 32, 17, None, None, 0, None) == _lib.MNK_ERR_ARG        # > MNK_MAX_SLAB_STEPS
+    assert L.mnk_step_slab(ctypes.byref(st), a, 32, a, 16, 2, None, None, 0, None) == _lib.MNK_ERR_ARG         # rd_stride < 5 * num_envs
+    assert L.mnk_step_slab(ctypes.byref(st), a, 8, a, 32, 2, None, None, 0, None) == _lib.MNK_ERR_ARG          # action_stride < 8 * num_envs
+    assert L.mnk_conv_tower(ctypes.byref(st), None, 80, 11, 1, None, a, a, a, a, a, None, None) == _lib.MNK_ERR_NULL
+    assert L.mnk_conv_tower(ctypes.byref(st), None, 72, 11, 1, a, a, a, a, a, a, None, None) == _lib.MNK_ERR_ARG     # unsupported width
+    assert L.mnk_conv_tower(ctypes.byref(st), None, 80, 10, 1, a, a, a, a, a, a, None, None) == _lib.MNK_ERR_ARG     # residual needs odd layers
+    big = _lib.MnkState(19, 19, 5, 6, 4, addr, maddr)
+    assert L.mnk_conv_tower(ctypes.byref(big), None, 96, 8, 0, a, a, a, a, a, a, None, None) == _lib.MNK_ERR_GEOM    # 401 rows > 384
+    assert L.mnk_transformer_body(ctypes.byref(st), None, 64, 4, 2, a, a, a, a, a, a, a, a, None, None) == _lib.MNK_ERR_ARG
+    assert L.mnk_transformer_body(ctypes.byref(st), None, 56, 4, 0, a, a, a, a, a, a, a, a, None, None) == _lib.MNK_ERR_ARG
+    mid = _lib.MnkState(13, 13, 5, 3, 4, addr, maddr)
+    assert L.mnk_transformer_body(ctypes.byref(mid), None, 56, 4, 2, a, a, a, a, a, a, a, a, None, None) == _lib.MNK_ERR_GEOM   # 169 tokens
+    assert L.mnk_transformer_layer_weight_bytes(56, 4) == 2 * (64 * 192 + 64 * 64 + 64 * 224 + 224 * 64)
+    assert L.mnk_transformer_layer_weight_bytes(96, 8) == 2 * (96 * 384 + 128 * 96 + 96 * 384 + 384 * 96)
+    assert L.mnk_transformer_layer_weight_bytes(64, 4) == _lib.MNK_ERR_ARG
+    assert L.mnk_resnet_tower_train_scratch_bytes(13, 13, 100, 4) == _lib.MNK_ERR_GEOM                               # board rows 3 .. 10
 
 
 def test_no_cpu_fallback():
