@@ -432,3 +432,35 @@ def test_step_slab_equals_consecutive_steps(m, n, k, ne):
     with pytest.raises(ValueError):
         _lib.check(L.mnk_step_slab(ctypes.byref(b_env._st), acts.data_ptr(), 8 * ne, rd.data_ptr(), rd_stride, 17, None, None, 0,
                                    torch.cuda.current_stream().cuda_stream), "mnk_step_slab")
+
+
+def test_fuzzed_geometries_against_the_oracle():
+    """Forty random (m, n, k, envs) -- every word count 1..8, n up to 32, k from 1 to min(m, n), env counts around the 32-env
+    tile -- through the dynamic-geometry kernels, a short game each, bit-exact against the C oracle (planes, mask, rewards,
+    dones, counters).  The parametrised test above fixes eleven geometries; this one widens the net."""
+    rng = np.random.default_rng(20261019)
+    seen_words = set()
+    for trial in range(40):
+        while True:
+            m, n = int(rng.integers(1, 17)), int(rng.integers(1, 33))
+            if m * (n + 1) <= 512:
+                break
+        k = int(rng.integers(1, min(m, n) + 1))
+        ne = int(rng.choice([1, 31, 32, 33, 63, 65, 100, 257]))
+        env = make_env(m, n, k, ne)
+        seen_words.add(env.words if hasattr(env, "words") else -1)
+        ref = orc.OracleEnv(m, n, k, ne)
+        obs = env.reset()
+        ref.reset()
+        for step in range(min(m * n + 2, 60)):
+            a = env.random_legal_actions(seed=trial, counter=step)
+            obs, r, d = env.step_autoreset(a)
+            o2, r2, d2 = ref.step(a.cpu().numpy())
+            assert np.array_equal(r.cpu().numpy(), r2) and np.array_equal(d.cpu().numpy(), d2), (m, n, k, ne, step)
+            assert np.array_equal(obs["observation"].cpu().numpy(), o2["observation"]), (m, n, k, ne, step)
+            assert np.array_equal(obs["action_mask"].cpu().numpy(), o2["action_mask"]), (m, n, k, ne, step)
+            done_idx = np.nonzero(d2)[0]
+            if len(done_idx):
+                ref.reset(done_idx)
+        assert np.array_equal(env.boards.cpu().numpy(), ref.boards.astype(np.float32)), (m, n, k, ne)
+        assert np.array_equal(env.move_counts.cpu().numpy(), ref.move_counts), (m, n, k, ne)
