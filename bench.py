@@ -816,6 +816,95 @@ def bench_rollout(ctx: Ctx, args, envs: int, agent_bn: str, extras: bool = True)
 
 
 # ------------------------------------------------------------------------------------------------
+# B200 arm: cfg1, the reference's own CPU-runnable case through the self-play wrapper
+# ------------------------------------------------------------------------------------------------
+def bench_wrapper_cfg1(ctx: Ctx, args):
+    """BASELINE configs[0] / SURVEY 8d cfg1: 3x3x3, 1,024 envs per GPU, RandomPolicy as agent AND opponent through
+    TorchSelfPlayWrapper (reset of finished games, side draw, opponent turn, zero-sum rewards, canonical obs + mask), 300
+    steps after warm-up.  Here: one sampler launch (the agent's RandomPolicy.act on the returned mask) + ONE fused wrapper
+    launch per step (mnk_selfplay_step_random), eager and as one CUDA graph; the CPU figure is the unmodified reference
+    running the same loop on the host.  Launch-bound at this size by construction -- the line shows the wrapper path at the
+    reference's default scale, not a roofline."""
+    torch = ctx.torch
+    from mnk_b200 import RandomPolicy, TorchSelfPlayWrapper, TorchVectorMnkEnv
+    m, n, k, envs, steps = 3, 3, 3, 1024, 300
+    env = TorchVectorMnkEnv(m, n, k, envs, device=f"cuda:{ctx.local_rank}", env_offset=ctx.rank * envs)
+    wr = TorchSelfPlayWrapper(env, seed=SEED)
+    wr.set_opponent(RandomPolicy(m * n, seed=5))
+    agent = RandomPolicy(m * n, seed=6)
+    obs, _ = wr.reset()
+    done_total = torch.zeros((), dtype=torch.float64, device=ctx.dev)
+
+    def one_step(o):
+        o, r, term, trunc, _ = wr.step(agent.act(o))
+        done_total.add_(term.sum())
+        return o
+
+    for _ in range(10):
+        obs = one_step(obs)
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        obs = one_step(obs)
+    e1.record()
+    ctx.barrier()
+    ms_eager = ctx.reduce([e0.elapsed_time(e1)], "max")[0]
+    finished = float(done_total.item())
+    # the same `steps` steps captured once as a CUDA graph (every launch of the path is capturable: no host synchronisation)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            o = obs
+            for _ in range(steps):
+                o = one_step(o)
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    ctx.barrier()
+    per = []
+    for _ in range(5):
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        per.append(e0.elapsed_time(e1))
+    ms_graph = ctx.reduce([statistics.median(per)], "max")[0]
+    line = {"metric": "self-play wrapper steps/sec (3x3x3, random vs random)", "value": envs * ctx.world * steps / (ms_eager * 1e-3),
+            "cuda_graph": {"value": envs * ctx.world * steps / (ms_graph * 1e-3), "unit": "agent-steps/s", "us_per_step": 1e3 * ms_graph / steps,
+                           "note": "the same loop replayed as one CUDA graph (what RolloutCollector.collect(graph=True) does): the eager "
+                                   "figure is bound by ~70 us of Python per step"},
+            "unit": "agent-steps/s", "n_gpus": ctx.world, "steps": steps, "warmup": 10, "ms_per_step": ms_eager / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "cfg1: tic-tac-toe 3x3x3, 1,024 envs per GPU, RandomPolicy agent and opponent through TorchSelfPlayWrapper "
+                                   "(f32 canonical observation + bool mask materialised every step), eager launches",
+                       "envs_per_gpu": envs, "l2": "the whole working set (37 KB of outputs per step) is cache-resident: launch-bound"},
+            "gpu_launches": 2 * steps, "episodes_finished": finished}
+    if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_tree
+        if ref_tree.available():
+            env_mod, wrap_mod, pol_mod = ref_tree.load("env.torch_vector_mnk_env", "selfplay.torch_self_play_wrapper", "selfplay.policy")
+            torch.set_num_threads(os.cpu_count() or 1)
+            torch.manual_seed(0)
+            r_wr = wrap_mod.TorchSelfPlayWrapper(env_mod.TorchVectorMnkEnv(m, n, k, envs, device="cpu"))
+            r_wr.set_opponent(pol_mod.RandomPolicy(m * n))
+            r_agent = pol_mod.RandomPolicy(m * n)
+            o, _ = r_wr.reset()
+            for _ in range(3):
+                o, *_ = r_wr.step(r_agent.act(o))
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                o, *_ = r_wr.step(r_agent.act(o))
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": envs * steps / dt, "unit": "agent-steps/s", "cores": torch.get_num_threads(), "kind": "reference",
+                                    "sample": f"the same loop, {steps} steps x {envs} envs, through the unmodified reference (env, wrapper, "
+                                              f"RandomPolicy) with device='cpu' on {os.cpu_count()} host CPUs"}
+    del wr, env
+    return line if ctx.rank == 0 else None
+
+
+# ------------------------------------------------------------------------------------------------
 # B200 arm: the network forwards alone (every tcgen05 forward the package ships), samples/s
 # ------------------------------------------------------------------------------------------------
 def bench_forwards(ctx: Ctx, args, envs: int):
@@ -928,9 +1017,11 @@ def main():
             line = bench_env_workload(ctx, Workload("cfg2", ctx.world, args.envs), args, primary=True)
             if not args.no_secondary:
                 secondary = {}
-                for name in ("cfg3", "cfg4", "cfg5", "forwards"):
+                for name in ("cfg1", "cfg3", "cfg4", "cfg5", "forwards"):
                     try:
-                        if name == "cfg3":
+                        if name == "cfg1":
+                            sec = bench_wrapper_cfg1(ctx, args)
+                        elif name == "cfg3":
                             sec = bench_rollout(ctx, args, args.rollout_envs, args.agent_bn)
                         elif name == "forwards":
                             sec = bench_forwards(ctx, args, args.rollout_envs)
