@@ -326,7 +326,7 @@ int mnk_resnet_tower_rows(const mnk_state_t* st, const uint8_t* swap, const void
 /* The same tower with TRAIN-MODE BatchNorm, as the reference's rollout forward runs it (src/alg/ppo.py:97 calls the
  * network without .eval(); BatchNorm2d of src/alg/architectures/resnet.py:9-21,27-31): every layer normalises with the
  * mean / biased variance of THIS batch over (envs, rows, columns) and updates running_mean / running_var in place
- * (momentum, unbiased variance), exactly one conv layer per kernel launch (csrc/mnk_resnet_train.cu), 3 <= m <= 10.
+ * (momentum, unbiased variance), exactly one conv layer per kernel launch (csrc/mnk_resnet_train.cu), 3 <= m <= 13.
  *   weights_rows  op16 [1+2*blocks][3 kx][4 k-chunks][ky*32 + c_out][8 c_in]: the UNFOLDED conv weights
  *   bn            per-layer BatchNorm parameters and statistics, f32 [1+2*blocks][32] each (layer 0 = conv_in, then
  *                 conv1 / conv2 of every block); batch_stats (may be NULL) receives f32 [1+2*blocks][64]: the batch

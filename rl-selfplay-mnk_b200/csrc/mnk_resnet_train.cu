@@ -36,9 +36,9 @@ using namespace mnk_umma;
 constexpr int kC = 32;
 constexpr int kChunks = kC / 8;
 constexpr int kN = 3 * kC;
-constexpr int kMaxBoardRows = 10;
+constexpr int kMaxBoardRows = 13;             // shared memory: 2 group buffers of 8 KB per board row next to 18 KB of weights
 constexpr int kMinBoardRows = 3;
-constexpr int kPad = 8;
+constexpr int kPad = 8;                       // zero rows before / after each operand plane; 1 for boards above 10 rows (shared memory)
 constexpr int kSlots = 5;
 constexpr int kTmemCols = 512;
 constexpr int kLead = 4;
@@ -70,7 +70,6 @@ struct Smem {
     alignas(128) unsigned char wts[kLayerWeightBytes];
     alignas(16) float scale[kC];
     float shift[kC];
-    float red[kEpiWarps][32];
     alignas(8) unsigned long long mma_bar[kSlots];
     unsigned long long wts_bar;
     unsigned long long in_bar[2];
@@ -79,11 +78,12 @@ struct Smem {
 #ifdef MNK_PROGRESS
     volatile unsigned int prog[24];           // debug build: (index << 4 | stage) of every warp, dumped on a watcher timeout
 #endif
-    alignas(128) unsigned char act[1];        // [2 buffers][4 k-chunks][m*128 + 2*kPad rows][16 B]
+    alignas(128) unsigned char act[1];        // [2 buffers][4 k-chunks][m*128 + 2*pad rows][16 B]
 };
 
 struct Params {
     int m, n, words, layer;
+    int pad;                          // zero rows before / after each operand plane
     long long num_envs, groups;
     int epc, pw;
     int reverse;                      // walk the groups from the last to the first
@@ -153,9 +153,12 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m = p.m;
-    const int plane16 = m * 128 + 2 * kPad;                  // rows (16-byte units) per k-chunk plane
+    const int pad = p.pad;
+    const int plane16 = m * 128 + 2 * pad;                   // rows (16-byte units) per k-chunk plane
     const int buf16 = kChunks * plane16;                     // 16-byte units per operand buffer
     uint4* const act = reinterpret_cast<uint4*>(&sm.act[0]);
+    // per-warp channel sums, written after the CTA's last MMA has completed: they reuse the weight buffer
+    float (*const red)[32] = reinterpret_cast<float (*)[32]>(&sm.wts[0]);
     constexpr bool first = kFirst;
     const int my_groups = (int)((p.groups - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const size_t plane_bytes = (size_t)m * 128 * 16;
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
                 const unsigned char* src = p.z_in + (size_t)group_of(i) * group_bytes;
                 mbar_expect_tx(&sm.in_bar[i], (u32)group_bytes);
                 for (int c = 0; c < kChunks; ++c)
-                    tma_bulk_g2s(act + i * buf16 + c * plane16 + kPad, src + c * plane_bytes, (u32)plane_bytes, &sm.in_bar[i]);
+                    tma_bulk_g2s(act + i * buf16 + c * plane16 + pad, src + c * plane_bytes, (u32)plane_bytes, &sm.in_bar[i]);
             }
         }
     }
@@ -195,10 +198,10 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
         const uint4 zero = make_uint4(0, 0, 0, 0);
         if (first) {   // k-chunks 0-1 of both buffers (the decode sets the stones of chunk 0; chunk 1 stays zero)
             for (int i = tid; i < 2 * 2 * plane16; i += kThreads) act[(i / (2 * plane16)) * buf16 + i % (2 * plane16)] = zero;
-        } else {       // the pad rows of all eight planes (the bulk copies fill rows kPad .. kPad + m*128)
-            for (int i = tid; i < 2 * kChunks * 2 * kPad; i += kThreads) {
-                const int plane = i / (2 * kPad), r = i % (2 * kPad);
-                act[plane * plane16 + (r < kPad ? r : m * 128 + r)] = zero;
+        } else {       // the pad rows of all eight planes (the bulk copies fill rows pad .. pad + m*128)
+            for (int i = tid; i < 2 * kChunks * 2 * pad; i += kThreads) {
+                const int plane = i / (2 * pad), r = i % (2 * pad);
+                act[plane * plane16 + (r < pad ? r : m * 128 + r)] = zero;
             }
             if (tid < 2 * kC) (&sm.scale[0])[tid] = p.in_scale_shift[tid];     // scale[32] then shift[32]
         }
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
         if (!ok && p.error != nullptr) atomicMax(p.error, 0x100 | p.layer);
         const u64 b_d0 = umma_desc(smem_u32(&sm.wts[0]), kN * 16, 128);
         const u32 b_lo0 = (u32)b_d0, b_hi = (u32)(b_d0 >> 32);
-        const u32 act_lo = smem_u32(&sm.act[0]) + kPad * 16;
+        const u32 act_lo = smem_u32(&sm.act[0]) + (u32)pad * 16;
         asm volatile("bar.sync %0, %1;" ::"r"(kReadyBarrier), "r"(kEpiThreads + 32) : "memory");   // rows 0 .. lead-1 of group 0
         int g = 0;
         for (int i = 0; i < my_groups; ++i) {
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
                 if (!first && b == lead - 1 && i >= 1 && i + 1 < my_groups && elect_one()) {
                     // step (i-1, m-1) is released: every MMA that read buffer (i+1) & 1 (group i-1) has completed
                     const size_t goff = (size_t)group_of(i + 1) * group_bytes;
-                    uint4* dst = act + (buf ^ 1) * buf16 + kPad;
+                    uint4* dst = act + (buf ^ 1) * buf16 + pad;
                     mbar_expect_tx(&sm.in_bar[buf ^ 1], (u32)group_bytes);
                     for (int c = 0; c < kChunks; ++c)
                         tma_bulk_g2s(dst + c * plane16, p.z_in + goff + c * plane_bytes, (u32)plane_bytes, &sm.in_bar[buf ^ 1]);
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
         const int t_c0 = tis >> 7, t_pos = tis & 127;
         const int t_s = t_pos / p.pw, t_c = t_pos - t_s * p.pw;
         const bool t_lane_ok = t_s < p.epc && t_c < p.n;
-        uint4* const unit0 = act + t_c0 * plane16 + kPad + t_pos;        // this thread's unit of row 0, buffer 0, first k-chunk
+        uint4* const unit0 = act + t_c0 * plane16 + pad + t_pos;        // this thread's unit of row 0, buffer 0, first k-chunk
         const size_t t_off = (size_t)t_c0 * plane_bytes + (size_t)t_pos * 16;    // the same unit inside a group in HBM
         const size_t e_off = (size_t)(2 * half) * plane_bytes + (size_t)pos * 16;
         // producer-side group state (group jt of the operand row being produced) and epilogue-side (group j)
@@ -509,8 +512,8 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
         if (lane == 0) {
 #pragma unroll
             for (int ch = 0; ch < 16; ++ch) {
-                sm.red[warp][ch] = s1[ch];
-                sm.red[warp][16 + ch] = s2[ch];
+                red[warp][ch] = s1[ch];
+                red[warp][16 + ch] = s2[ch];
             }
         }
     }
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) resnet_layer_train_kernel(Params 
         const int which = tid >> 5, ch = tid & 31, half = ch >> 4;
         float acc = 0.0f;
         for (int w = 0; w < kEpiWarps; ++w)
-            if (((w >> 2) & 1) == half) acc += sm.red[w][which * 16 + (ch & 15)];
+            if (((w >> 2) & 1) == half) acc += red[w][which * 16 + (ch & 15)];
         p.partials[(size_t)blockIdx.x * 64 + tid] = acc;
         __threadfence();
     }
@@ -670,7 +673,9 @@ extern "C" int mnk_resnet_tower_train(const mnk_state_t* st, const uint8_t* swap
     // timeout since the caller zeroed the scratch buffer, so a failure inside a long captured rollout can still be read
     cudaError_t e = cudaMemsetAsync(base + lay.counter, 0, 64, s);
     if (e != cudaSuccess) return (int)e;
-    const size_t smem = sizeof(rt::Smem) + 128 + (size_t)2 * rt::kChunks * (st->m * 128 + 2 * rt::kPad) * 16;
+    const int pad = st->m <= 10 ? rt::kPad : 1;
+    const size_t smem = sizeof(rt::Smem) + 128 + (size_t)2 * rt::kChunks * (st->m * 128 + 2 * pad) * 16;
+    if (smem > 227 * 1024) return MNK_ERR_GEOM;
     static std::atomic<size_t> granted[5][kMaxDevices];
     if (int rc = mnk_optin_smem(rt::resnet_layer_train_kernel<true, false, false>, smem, granted[0])) return rc;
     if (int rc = mnk_optin_smem(rt::resnet_layer_train_kernel<false, true, true>, smem, granted[1])) return rc;
@@ -679,7 +684,7 @@ extern "C" int mnk_resnet_tower_train(const mnk_state_t* st, const uint8_t* swap
     if (int rc = mnk_optin_smem(rt::resnet_layer_train_kernel<false, false, false>, smem, granted[4])) return rc;
     for (int L = 0; L < layers; ++L) {
         rt::Params p;
-        p.m = st->m; p.n = st->n; p.words = st->words; p.layer = L;
+        p.m = st->m; p.n = st->n; p.words = st->words; p.layer = L; p.pad = pad;
         p.num_envs = st->num_envs; p.groups = lay.groups;
         p.pw = st->n + 1; p.epc = 128 / p.pw;
         p.reverse = L & 1;

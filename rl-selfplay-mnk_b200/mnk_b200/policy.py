@@ -87,6 +87,9 @@ class NNPolicy(Policy):
         """Action for the side to move of every env, straight from the bitboards (the wrapper's dense opponent call)."""
         swap = (env._meta & 1).to(torch.uint8)
         logits, _ = self._fresh_net().forward_env(env, swap, want_value=False)
+        self._native_calls = getattr(self, "_native_calls", 0) + 1
+        if self._native_calls % 512 == 0 and not torch.cuda.is_current_stream_capturing():
+            self.net.check_error()           # one host read every 512 calls: a barrier timeout must not pass silently
         return masked_sample(logits, env.legal_mask(), seed=self.seed, counter=counter, row_offset=env.env_offset,
                              deterministic=deterministic, want_log_prob=False, counter_base=self.counter_base)[0]
 

@@ -65,7 +65,7 @@ class PPOAgent:
         if world_size > 1:          # replicas start from rank 0's parameters / buffers / optimiser state
             broadcast_module(self.network, self.optimizer, group=process_group)
         # Rollout forward on the tcgen05 path with the semantics of the reference's rollout, which never leaves train mode
-        # (src/alg/ppo.py:97): TRAIN-mode BatchNorm for the default architecture (resnet_b_s layout, boards up to 10 rows);
+        # (src/alg/ppo.py:97): TRAIN-mode BatchNorm for the default architecture (resnet_b_s layout, boards up to 13 rows);
         # the transformers have neither BatchNorm nor dropout, so their native forward is already exact.  Any other module
         # keeps the generic path (stock PyTorch forward on f32 observations).
         self.native, self.graph_rollout = None, graph_rollout
@@ -75,7 +75,7 @@ class PPOAgent:
             try:
                 if transformer.supports(self.network):
                     self.native = transformer.NativeTransformer(self.network, device=self.device)
-                elif obs_shape[1] <= 10:
+                elif obs_shape[1] <= 13:
                     self.native = NativeResNet(self.network, device=self.device, bn_mode="train")
             except (ValueError, AttributeError):
                 self.native = None

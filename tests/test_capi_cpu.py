@@ -78,7 +78,8 @@ def test_argument_validation_without_gpu():
     assert L.mnk_transformer_layer_weight_bytes(56, 4) == 2 * (64 * 192 + 64 * 64 + 64 * 224 + 224 * 64)
     assert L.mnk_transformer_layer_weight_bytes(96, 8) == 2 * (96 * 384 + 128 * 96 + 96 * 384 + 384 * 96)
     assert L.mnk_transformer_layer_weight_bytes(64, 4) == _lib.MNK_ERR_ARG
-    assert L.mnk_resnet_tower_train_scratch_bytes(13, 13, 100, 4) == _lib.MNK_ERR_GEOM                               # board rows 3 .. 10
+    assert L.mnk_resnet_tower_train_scratch_bytes(14, 14, 100, 4) == _lib.MNK_ERR_GEOM                               # board rows 3 .. 13
+    assert L.mnk_resnet_tower_train_scratch_bytes(13, 13, 100, 4) > 0
 
 
 def test_no_cpu_fallback():

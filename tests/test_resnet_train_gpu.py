@@ -85,7 +85,8 @@ def test_train_mode_forward_matches_reference_fixture(path):
 
 
 @pytest.mark.parametrize("m,n,k,counts", [(9, 9, 5, (1, 12, 13, 1777, 5000)), (3, 3, 3, (7, 4000)), (5, 7, 4, (333,)),
-                                          (10, 10, 5, (2500,)), (6, 22, 5, (1000,)), (7, 7, 4, (3000,))], ids=str)
+                                          (10, 10, 5, (2500,)), (6, 22, 5, (1000,)), (7, 7, 4, (3000,)),
+                                          (13, 13, 5, (1, 9, 10, 2000)), (11, 11, 5, (1500,)), (12, 7, 4, (3000,))], ids=str)
 def test_train_mode_forward_matches_torch_module(m, n, k, counts):
     """Against the torch module (mnk_b200.nets.ResNetActorCritic == the reference network, tests/test_nets_cpu.py) in
     .train() on the GPU, on mid-game positions: env counts with a partial last group, one group per CTA and several
@@ -160,11 +161,11 @@ def test_train_mode_forward_matches_torch_module(m, n, k, counts):
 
 def test_train_mode_geometry_limits_and_eval_unchanged():
     from mnk_b200 import NativeResNet, ResNetActorCritic, TorchVectorMnkEnv
-    net = ResNetActorCritic((2, 13, 13), 169).to(DEV)
+    net = ResNetActorCritic((2, 15, 15), 225).to(DEV)
     native = NativeResNet(net, device=DEV, bn_mode="train")
-    env = TorchVectorMnkEnv(13, 13, 5, 10, device=DEV)
+    env = TorchVectorMnkEnv(15, 15, 5, 10, device=DEV)
     env.reset()
-    with pytest.raises(ValueError):      # boards with more than 10 rows: train-mode kernel not available
+    with pytest.raises(ValueError):      # boards with more than 13 rows: train-mode kernel not available (shared memory)
         native.forward_env(env)
     with pytest.raises(ValueError):
         NativeResNet(net, device=DEV, bn_mode="batch")

@@ -176,3 +176,30 @@ def test_graph_rollout_with_wide_and_transformer_networks(agent_arch, opp_arch):
         seen.append(buf.actions[:steps].clone())
     assert not torch.equal(seen[0], seen[1]) and col._graph_replays == 3
     agent.check_error(), opp.net.check_error()
+
+
+def test_rollout_on_13x13_with_the_train_mode_tower():
+    """The board of the reference's second experiment (src/train_all_13.py): the agent's forward on mnk_resnet_tower_train
+    (boards up to 13 rows), the frozen opponent on the tap kernel; eager and as a graph: legal actions, finite statistics,
+    running statistics moving, flags clean."""
+    import copy
+    from mnk_b200 import NativeNNPolicy, NativeResNet, ResNetActorCritic, RolloutBuffer, RolloutCollector, TorchSelfPlayWrapper, TorchVectorMnkEnv
+    torch.manual_seed(8)
+    m, n, k, ne, steps = 13, 13, 5, 300, 5
+    net = ResNetActorCritic((2, m, n), m * n).to(DEV)
+    agent = NativeResNet(net, device=DEV, bn_mode="train")
+    before = agent._params["running_mean"].clone()
+    wr = TorchSelfPlayWrapper(TorchVectorMnkEnv(m, n, k, ne, device=DEV), seed=2)
+    wr.set_opponent(NativeNNPolicy(copy.deepcopy(net), seed=3))
+    buf = RolloutBuffer(steps, ne, (2, m, n), m * n, device=DEV, k=k)
+    col = RolloutCollector(ne, device=DEV, seed=4)
+    wr.reset(materialise=False)
+    col._last_obs = {"observation": None, "action_mask": None}
+    for graph in (False, True, True):
+        buf.reset()
+        stats = col.collect(agent, wr, buf, graph=graph)
+        assert stats.agent_steps == steps * ne
+        assert bool(buf.action_masks.gather(2, buf.actions[:steps].unsqueeze(-1)).all())
+        assert bool(torch.isfinite(buf.log_probs[:steps]).all()) and bool(torch.isfinite(buf.values[:steps]).all())
+    assert not torch.equal(before, agent._params["running_mean"])
+    agent.check_error(), wr.opponent_policy.net.check_error()
