@@ -115,7 +115,7 @@ def pin_to_gpu_numa(local_rank: int):
         with open(path) as f:
             node = int(f.read().strip())
         if node < 0:
-            return None
+            raise LookupError("no numa_node")
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             spec = f.read().strip()
         cpus = set()
@@ -124,8 +124,26 @@ def pin_to_gpu_numa(local_rank: int):
             cpus.update(range(int(lo), int(hi or lo) + 1))
         allowed = cpus & os.sched_getaffinity(0)
         if not allowed:
-            return None
+            raise LookupError("empty cpu list")
         os.sched_setaffinity(0, allowed)
         return f"numa node {node}: {len(allowed)} cpus"
+    except Exception:
+        pass
+    try:        # containers often hide the PCI device's numa_node: ask the driver for the GPU's ideal CPUs instead
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(torch.cuda.get_device_properties(local_rank).pci_bus_id_str
+                                                      if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id_str")
+                                                      else f"{torch.cuda.get_device_properties(local_rank).pci_domain_id:08x}:"
+                                                           f"{torch.cuda.get_device_properties(local_rank).pci_bus_id:02x}:"
+                                                           f"{torch.cuda.get_device_properties(local_rank).pci_device_id:02x}.0")
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed or allowed == os.sched_getaffinity(0):
+            return None
+        os.sched_setaffinity(0, allowed)
+        return f"nvml cpu affinity: {len(allowed)} cpus"
     except Exception:
         return None
