@@ -170,3 +170,28 @@ def test_transformer_agent_rolls_out_on_the_native_forward():
     m = agent.learn(wr)
     assert np.isfinite(m.actor_loss) and np.isfinite(m.critic_loss) and m.fps > 0
     assert agent.native.version == version + 1 and stats.agent_steps == steps * ne
+
+
+@pytest.mark.parametrize("arch", ["cnn_b_s", "resnet_b_l"])
+def test_wide_conv_agents_train_on_the_generic_rollout_path(arch):
+    """The wide convolutional agents have a BatchNorm body and no train-mode kernel: PPOAgent keeps the stock module for the
+    agent's rollout forward (reference semantics) while the opponent runs on mnk_conv_tower through the drop-in NNPolicy."""
+    from mnk_b200 import NativeConvNet, PPOAgent, TorchSelfPlayWrapper, TorchVectorMnkEnv, build_architecture
+    from selfplay.policy import NNPolicy
+    import copy
+    torch.manual_seed(0)
+    ne, steps = 128, 4
+    env = TorchVectorMnkEnv(5, 5, 4, ne, device=DEV)
+    wr = TorchSelfPlayWrapper(env, seed=1)
+    net = build_architecture(arch, (2, 5, 5), 25).to(DEV)
+    opp = NNPolicy(copy.deepcopy(net))
+    assert isinstance(opp.net, NativeConvNet)
+    wr.set_opponent(opp)
+    agent = PPOAgent((2, 5, 5), 25, net, n_steps=steps, optimizer=torch.optim.AdamW(net.parameters(), lr=1e-3), batch_size=256,
+                     ppo_epochs=1, num_envs=ne, device=DEV, k=4)
+    assert agent.native is None
+    net.train()
+    for _ in range(2):
+        m = agent.learn(wr)
+        assert np.isfinite(m.actor_loss) and np.isfinite(m.critic_loss) and m.fps > 0
+    opp.net.check_error()
